@@ -1,0 +1,369 @@
+#!/usr/bin/env python3
+"""Benchmark of the feature-extraction hot path (BASELINE.json metric: clips/s of 1 s, 16 kHz int16 clips).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of 512 synthetic clips (BASELINE config 2, train.py's default
+batch) per GPU: a single fused kernel launch.  Prints ONE JSON line on rank 0.
+
+  value         whole-job clips/s, inputs resident in HBM, CUDA events around exactly K back-to-back steps,
+                max over ranks.  A pool of distinct input batches larger than L2 is rotated so that no step finds
+                its input in L2.
+  e2e           same metric through the public host-buffer API (plan.extract_host -> scf_extract_host_i16):
+                pinned host int16 in, H2D + kernel + D2H inside the timed region, every step.
+  roofline      the kernel against the measured HBM peak (algorithmic 34,400 B per clip) and, under "fp32", against
+                the FP32 compute roofline that actually binds (925,200 algorithmic FLOP per clip; peak = FMA
+                micro-benchmark measured in this run, nominal 74.45 TFLOP/s beside it).
+  cpu_baseline  the oracle's numpy restatement of the reference's sonopy path on the host cores (bounded sample).
+
+--impl reference times the reference's own CPU implementation of the path: the numpy/sonopy restatement in
+oracle/ (sonopy itself is not installable offline) over all host cores; the compiled in-tree C++ twin
+(oracle/_ref, inference/tflite/mfcc.h) is timed beside it on one thread.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIPS_PER_STEP = 512
+CLIP_LEN = 16000
+FRAMES = 30
+COLS = 20
+BYTES_PER_CLIP = 32000 + 2400
+FLOPS_PER_CLIP = 925200
+FP32_NOMINAL = 148 * 128 * 2 * 1.965e9
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clocks and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._busy = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for k in dir(nv):
+            if k.startswith('nvmlClocksEventReason') or k.startswith('nvmlClocksThrottleReason'):
+                v = getattr(nv, k)
+                if isinstance(v, int) and v not in (0,):
+                    names.setdefault(v, k.replace('nvmlClocksEventReason', '').replace('nvmlClocksThrottleReason', ''))
+        while not self._stop.is_set():
+            if self._busy.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if bit and (r & bit) == bit and bin(bit).count('1') == 1:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+
+    def busy(self, on):
+        (self._busy.set if on else self._busy.clear)()
+
+    def stop(self):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join(timeout=1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        reasons = sorted(x for x in self.reasons if x not in ('GpuIdle', 'None', 'ApplicationsClocksSetting'))
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker_init():
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = '1'
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def _cpu_chunk(pcm):
+    import numpy as np
+    from oracle import sonopy as osonopy
+    out = np.empty((len(pcm), FRAMES, COLS), dtype=np.float32)
+    for i, c in enumerate(pcm):
+        out[i] = osonopy.mfcc_spec(c.astype(np.float32) / 32768.0, 16000, (1024, 512), 1024, 20, 20)
+    return out
+
+
+def cpu_port_rate(pcm, pool, n_proc):
+    """clips/s of the oracle port over `pcm` using the given pool (or inline when pool is None)."""
+    import numpy as np
+    t0 = time.perf_counter()
+    if pool is None:
+        _cpu_chunk(pcm)
+    else:
+        parts = np.array_split(pcm, n_proc * 4)
+        pool.map(_cpu_chunk, [p for p in parts if len(p)])
+    return len(pcm) / (time.perf_counter() - t0)
+
+
+def cpp_twin_rate(pcm):
+    """clips/s of the compiled reference C++ (inference/tflite/mfcc.h) on one thread, or None."""
+    import ctypes
+    import numpy as np
+    path = os.path.join(ROOT, 'oracle', '_ref', 'libref_mfcc.so')
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.ref_mfcc.restype = ctypes.c_int
+    lib.ref_mfcc.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 9 + [ctypes.c_void_p]
+    out = np.zeros((FRAMES, COLS), dtype=np.float32)
+    t0 = time.perf_counter()
+    for c in pcm:
+        a = np.ascontiguousarray(c.astype(np.float32) / 32768.0)
+        lib.ref_mfcc(a.ctypes.data, len(a), 16000, 1024, 512, 1024, 20, 20, 0, 16000, 0, out.ctypes.data)
+    return len(pcm) / (time.perf_counter() - t0)
+
+
+def run_cpu_baseline(seconds=12.0):
+    """Bounded sample of the same workload on the host cores; returns the cpu_baseline object."""
+    import multiprocessing as mp
+    import numpy as np
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32768, size=(CLIPS_PER_STEP, CLIP_LEN), dtype=np.int16)
+    n_proc = len(os.sched_getaffinity(0))
+    _cpu_worker_init()
+    r1 = cpu_port_rate(pcm[:64], None, 1)                       # warm-up + calibration
+    n1 = int(max(64, min(4096, r1 * seconds * 0.25)))
+    single = cpu_port_rate(np.tile(pcm, (n1 // 512 + 1, 1))[:n1], None, 1)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(n_proc, initializer=_cpu_worker_init) as pool:
+        cpu_port_rate(pcm, pool, n_proc)                        # warm the workers
+        n = int(max(512, min(65536, single * n_proc * seconds * 0.6)))
+        big = np.tile(pcm, (n // 512 + 1, 1))[:n]
+        multi = cpu_port_rate(big, pool, n_proc)
+    cpp = cpp_twin_rate(pcm[:32])
+    return {'value': multi, 'unit': 'clips/s', 'cores': n_proc, 'kind': 'port',
+            'sample': '%d clips of the 512-clip uniform-int16 batch (tiled), oracle/sonopy.py float64 numpy port of '
+                      'sonopy.mfcc_spec in %d processes with BLAS threads pinned to 1' % (n, n_proc),
+            'single_core_value': single,
+            'reference_cpp_mfcc_h_1thread_value': cpp}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import numpy as np
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32768, size=(CLIPS_PER_STEP, CLIP_LEN), dtype=np.int16)
+    n_proc = len(os.sched_getaffinity(0))
+    _cpu_worker_init()
+    ctx = mp.get_context('fork')
+    with ctx.Pool(n_proc, initializer=_cpu_worker_init) as pool:
+        est = cpu_port_rate(pcm, pool, n_proc)                  # also warms the workers
+        budget_clips = est * 90.0                               # keep the whole run near 1.5 minutes at most
+        per_step = int(max(n_proc * 4, min(CLIPS_PER_STEP, budget_clips / max(1, args.steps + args.warmup))))
+        sample = pcm[:per_step]
+        for _ in range(args.warmup):
+            cpu_port_rate(sample, pool, n_proc)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            parts = np.array_split(sample, n_proc * 4)
+            pool.map(_cpu_chunk, [p for p in parts if len(p)])
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    cpp = cpp_twin_rate(pcm[:32])
+    line = {
+        'impl': 'reference', 'metric': 'features clips/sec (1 s, 16 kHz)', 'value': value, 'unit': 'clips/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: batch of 512 synthetic 1 s 16 kHz int16 clips, params.json MFCC (30x20)',
+                   'sample_clips_per_step': per_step},
+        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': n_proc, 'kind': 'port',
+                         'sample': '%d clips per step; numpy restatement (oracle/sonopy.py) of the reference Python path '
+                                   'common/data_utils.py:69 -> sonopy.mfcc_spec, %d processes' % (per_step, n_proc),
+                         'reference_cpp_mfcc_h_1thread_value': cpp},
+        'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import scfeat
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: libscfeat has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    plan = scfeat.get_plan(device=local_rank)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- inputs: a pool of distinct batches larger than L2 (126 MB), resident in HBM ------------------------
+    n_pool = 16                                                   # 16 x 16.4 MB = 262 MB
+    rng = np.random.default_rng(1000 + rank)
+    host_pool = rng.integers(-32768, 32768, size=(n_pool, CLIPS_PER_STEP, CLIP_LEN), dtype=np.int16)
+    d_pool = torch.from_numpy(host_pool).cuda()
+    d_out = torch.empty((CLIPS_PER_STEP, FRAMES, COLS), dtype=torch.float32, device='cuda')
+    st = torch.cuda.Stream()
+    ptrs = [d_pool[i].data_ptr() for i in range(n_pool)]
+
+    def step(i):
+        plan.extract_device(ptrs[i % n_pool], CLIPS_PER_STEP, CLIP_LEN, d_out.data_ptr(), stream=st.cuda_stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    fp32_peak = scfeat.measure_fp32_flops(local_rank)
+
+    with torch.cuda.stream(st):
+        for i in range(W):
+            step(i)
+        barrier()
+        launches0 = scfeat.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.busy(True)
+        e0.record(st)
+        for i in range(K):
+            step(W + i)
+        e1.record(st)
+        barrier()
+        sampler.busy(False)
+        launches = scfeat.launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+
+    # parity spot check of the timed configuration (last batch computed) -- outside the timed region
+    got = d_out.cpu().numpy()
+
+    # ---- e2e: host buffers through the public API, H2D + kernel + D2H every step -----------------------------
+    n_hpool = 4
+    h_pin = torch.empty((n_hpool, CLIPS_PER_STEP, CLIP_LEN), dtype=torch.int16).pin_memory()
+    h_pin.numpy()[:] = host_pool[:n_hpool]
+    h_np = [h_pin[i].numpy() for i in range(n_hpool)]
+    Ke = max(10, min(K, 200))
+    for i in range(3):
+        plan.extract_host(h_np[i % n_hpool])
+    barrier()
+    sampler.busy(True)
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        feats = plan.extract_host(h_np[i % n_hpool])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.busy(False)
+    sampler.stop()
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        peaks, peaks_src = read_peaks()
+        clips_per_s = world * CLIPS_PER_STEP * K / (ms * 1e-3)
+        launch_s = ms * 1e-3 / K
+        hbm_achieved = CLIPS_PER_STEP * BYTES_PER_CLIP / launch_s / 1e9
+        fp32_achieved = CLIPS_PER_STEP * FLOPS_PER_CLIP / launch_s
+        cpu = run_cpu_baseline() if world == 1 else None
+        line = {
+            'metric': 'features clips/sec (1 s, 16 kHz)', 'value': clips_per_s, 'unit': 'clips/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: batch of 512 synthetic 1 s 16 kHz int16 clips per GPU, params.json MFCC '
+                                   '(window 1024, hop 512, n_fft 1024, 20 mel filters, 20 coefficients -> 30x20)',
+                       'clips_per_step_per_gpu': CLIPS_PER_STEP, 'parallelism': 'clip-sharded x%d, no collective' % world,
+                       'l2_policy': 'pool of 16 distinct 16.4 MB input batches (262 MB > 126 MB L2) rotated per step'},
+            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks_src,
+                         'kernel': 'scf::extract_kernel<32,int16,fast>', 'algorithmic_bytes_per_launch': CLIPS_PER_STEP * BYTES_PER_CLIP,
+                         'binding': 'fp32 (SURVEY 8d: 26.9 flop/B > machine balance), see "fp32"',
+                         'fp32': {'achieved': fp32_achieved / 1e12, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
+                                  'frac': fp32_achieved / fp32_peak, 'peak_source': 'FMA micro-benchmark in this run',
+                                  'nominal_peak': FP32_NOMINAL / 1e12, 'frac_of_nominal': fp32_achieved / FP32_NOMINAL,
+                                  'algorithmic_flops_per_launch': CLIPS_PER_STEP * FLOPS_PER_CLIP}},
+            'cpu_baseline': cpu,
+            'e2e': {'value': world * CLIPS_PER_STEP * Ke / (e2e_ms * 1e-3), 'unit': 'clips/s',
+                    'h2d_bytes_per_step': CLIPS_PER_STEP * CLIP_LEN * 2, 'd2h_bytes_per_step': CLIPS_PER_STEP * FRAMES * COLS * 4,
+                    'steps': Ke, 'api': 'Plan.extract_host -> scf_extract_host_i16 (pinned host int16 in, host float32 out)'},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'finite_output': bool(np.isfinite(got).all() and np.isfinite(feats).all()),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 5000 if args.steps is None else args.steps
+        args.warmup = 50 if args.warmup is None else args.warmup
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

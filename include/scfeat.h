@@ -1,0 +1,189 @@
+/*
+ * scfeat.h -- C ABI of libscfeat.so: batched speech-feature extraction on NVIDIA B200 (sm_100a).
+ *
+ *   int16/float PCM -> [pre-emphasis] -> framing/[window] -> real-FFT power spectrum
+ *   -> mel / Bark filterbank -> log -> DCT-II (MFCC / BFCC)
+ *
+ * Drop-in boundary for ONE hot path of david8862/tf-keras-speech-commands.  The reference has
+ * no FFI for this path (its boundary is a set of Python functions and a header-only C++ twin),
+ * so every entry point below names the reference interface it stands in for
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes / C++ binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 (SCF_OK) or a negative scf_status; nothing throws
+ * across the ABI; scf_last_error() returns a thread-local message for the last failure.
+ * Plans are immutable after creation and may be shared between threads; stream objects are
+ * single-owner.  "d_" pointers are device pointers on the plan's device, "h_" are host pointers.
+ * `cuda_stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device
+ * entry points are stream-ordered and never synchronise the host.
+ */
+#ifndef SCFEAT_H
+#define SCFEAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCF_VERSION 100
+
+typedef enum scf_status {
+    SCF_OK = 0,
+    SCF_ERR_INVALID = -1,      /* bad argument / unsupported configuration            */
+    SCF_ERR_CUDA = -2,         /* a CUDA runtime call failed (message has the detail) */
+    SCF_ERR_NO_DEVICE = -3,    /* no usable CUDA device: there is NO CPU fallback      */
+    SCF_ERR_ALLOC = -4,
+    SCF_ERR_NCCL = -5
+} scf_status;
+
+/* Filterbank family.
+ * SCF_BANK_MEL_SONOPY : sonopy.filterbanks(sample_rate, n_filt, n_fft/2+1) as used through
+ *                       common/data_utils.py:69; C++ twin inference/tflite/mfcc.h:230-264 called
+ *                       with low=0, high=sample_rate (inference/tflite/speech_commands.h:304-307).
+ * SCF_BANK_BARK_REF   : common/bark_feature.py:92-136 bark_filterbanks (incl. its quirk of mapping
+ *                       bins with nfft=512 / 16 kHz whatever the caller passes).
+ * SCF_BANK_CUSTOM     : caller-supplied dense [n_filt][n_fft/2+1] doubles. */
+typedef enum scf_bank_kind { SCF_BANK_MEL_SONOPY = 0, SCF_BANK_BARK_REF = 1, SCF_BANK_CUSTOM = 2 } scf_bank_kind;
+
+/* bark_filterbanks(scale=...) common/bark_feature.py:117-129 */
+typedef enum scf_bank_scale { SCF_SCALE_CONSTANT = 0, SCF_SCALE_ASCENDANT = 1, SCF_SCALE_DESCENDANT = 2 } scf_bank_scale;
+
+/* What one output row holds.
+ * SCF_OUT_POWER    : power_spec()            common/bark_feature.py:85-89   -> n_fft/2+1 columns
+ * SCF_OUT_LOG_BANK : mel_spec()/bark_spec()  common/bark_feature.py:139-153 -> n_filt columns
+ * SCF_OUT_CEPSTRUM : mfcc_spec()/bfcc_spec() common/bark_feature.py:156-175 -> min(n_filt,n_coeffs)
+ *                    columns, column 0 replaced by the log frame energy. */
+typedef enum scf_output_kind { SCF_OUT_POWER = 0, SCF_OUT_LOG_BANK = 1, SCF_OUT_CEPSTRUM = 2 } scf_output_kind;
+
+/* Analysis window.  The Python path uses none (rectangular); Hamming is the C++ twin's optional
+ * use_preprocess branch, inference/tflite/mfcc.h:394-410 (denominator window-1). */
+typedef enum scf_window_kind { SCF_WIN_RECT = 0, SCF_WIN_HAMMING = 1, SCF_WIN_HANN = 2 } scf_window_kind;
+
+/* How a clip shorter than clip_len is treated.
+ * SCF_PAD_FRONT_ZERO : audio_to_feature, common/data_utils.py:73-86 -- zeros in FRONT, every clip
+ *                      yields frames_per_clip(clip_len) rows.
+ * SCF_PAD_NONE       : vectorize_raw, common/data_utils.py:61-70 -- only frames that fit inside the
+ *                      clip's own length are produced; the remaining rows are left untouched. */
+typedef enum scf_pad_kind { SCF_PAD_FRONT_ZERO = 0, SCF_PAD_NONE = 1 } scf_pad_kind;
+
+typedef struct scf_config {
+    int32_t sample_rate;     /* classifier/params.py:52                    default 16000 */
+    int32_t window;          /* window_samples, classifier/params.py:70-73 default 1024  */
+    int32_t hop;             /* hop_samples,    classifier/params.py:75-78 default 512   */
+    int32_t n_fft;           /* 256, 512 or 1024                           default 1024  */
+    int32_t n_filt;          /* <= 64                                      default 20    */
+    int32_t n_coeffs;        /* n_mfcc                                     default 20    */
+    int32_t bank;            /* scf_bank_kind                                           */
+    int32_t bank_scale;      /* scf_bank_scale (Bark only)                               */
+    int32_t output;          /* scf_output_kind                                         */
+    int32_t window_fn;       /* scf_window_kind                            default RECT  */
+    float   preemph_alpha;   /* 0 = off; mfcc.h:396 uses 0.95; x[-1] := 0                */
+    float   pcm_scale;       /* int16 -> float factor, 1/32768 (common/data_utils.py:21); ignored for float input */
+    int32_t device;          /* CUDA device ordinal, -1 = current                        */
+    int32_t reserved;
+    const double* custom_bank; /* SCF_BANK_CUSTOM only                                   */
+} scf_config;
+
+typedef struct scf_plan scf_plan;
+typedef struct scf_stream scf_stream;
+
+/* ---- host-only helpers (no GPU needed) ------------------------------------------------- */
+
+/* Fills *cfg with configs/params.json (== classifier/params.py:99-103) MFCC settings. */
+int scf_config_default(scf_config* cfg);
+
+/* Number of frames chop_array yields for n_samples (common/bark_feature.py:80-82). */
+int64_t scf_num_frames(int64_t n_samples, int32_t window, int32_t hop);
+
+/* Output columns for this configuration (see scf_output_kind). */
+int32_t scf_out_cols(const scf_config* cfg);
+
+/* Dense float64 filterbank [n_filt][n_fft/2+1] exactly as the reference builds it. */
+int scf_build_bank(const scf_config* cfg, double* bank_out);
+
+/* DCT-II ortho matrix [n_filt][min(n_filt,n_coeffs)], scipy.fftpack.dct(norm='ortho') /
+ * inference/tflite/mfcc.h:42-71. */
+int scf_build_dct(int32_t n_filt, int32_t n_coeffs, double* dct_out);
+
+/* ---- plan ------------------------------------------------------------------------------ */
+
+/* Builds bank / DCT / twiddle / window tables in float64 on the host, uploads them.
+ * Fails with SCF_ERR_NO_DEVICE when no CUDA device is present. */
+int scf_plan_create(const scf_config* cfg, scf_plan** plan_out);
+void scf_plan_destroy(scf_plan* plan);
+int scf_plan_config(const scf_plan* plan, scf_config* cfg_out);
+
+/* ---- batched extraction: replaces the serial loop classifier/data.py:39-43 over
+ *      get_mfcc_feature (common/data_utils.py:89-97) and sonopy.mfcc_spec / bark_feature.*_spec -- */
+
+/* Clip i occupies d_pcm[i*clip_stride .. i*clip_stride + len_i) with len_i = d_lengths ? min(d_lengths[i],
+ * clip_len) : clip_len.  Row (i, f) of the output is written at d_out + (i*frames_per_clip + f)*out_cols
+ * where frames_per_clip = scf_num_frames(clip_len, window, hop). */
+int scf_extract_i16(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride,
+                    int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out, void* cuda_stream);
+
+/* Same for float audio already scaled to [-1, 1) (what the reference's Python functions take). */
+int scf_extract_f32(const scf_plan* plan, const float* d_audio, int64_t n_clips, int64_t clip_stride,
+                    int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out, void* cuda_stream);
+
+/* Host-buffer convenience wrappers (pinned staging, H2D, kernel, D2H, synchronous): what the
+ * numpy-in / numpy-out drop-in functions call.  h_lengths may be NULL. */
+int scf_extract_host_i16(const scf_plan* plan, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
+                         int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out);
+int scf_extract_host_f32(const scf_plan* plan, const float* h_audio, int64_t n_clips, int64_t clip_stride,
+                         int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out);
+
+/* Library-owned output handed over as a DLPack capsule payload: *dl_out is a DLManagedTensor*
+ * (kDLCUDA, float32, shape [n_clips, frames_per_clip, out_cols]) whose deleter frees the device
+ * buffer; consumable by tf.experimental.dlpack.from_dlpack / torch.from_dlpack. */
+int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride,
+                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, void** dl_out,
+                           void* cuda_stream);
+
+/* ---- streaming: replaces Listener.update_vectors, listen.py:96-114 (C++ twin
+ *      inference/tflite/speech_commands.h:355-449), for n_streams concurrent listeners -------- */
+
+/* ring_rows = pr.n_features (classifier/params.py:65-68); max_chunk = largest chunk (samples) a
+ * push may carry.  Rings start as zeros, carries empty (listen.py:90-92). */
+int scf_stream_create(const scf_plan* plan, int32_t n_streams, int32_t ring_rows, int32_t max_chunk,
+                      scf_stream** stream_out);
+void scf_stream_destroy(scf_stream* s);
+int scf_stream_reset(scf_stream* s, void* cuda_stream);
+
+/* d_chunks: [n_streams][chunk_len] int16.  After the call (stream-ordered) d_ring_out, if not NULL,
+ * holds [n_streams][ring_rows][out_cols] oldest->newest; d_new_rows, if not NULL, the number of frames
+ * each stream emitted this step. */
+int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_len, float* d_ring_out,
+                        int32_t* d_new_rows, void* cuda_stream);
+int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chunk_len, float* h_ring_out,
+                             int32_t* h_new_rows);
+
+/* ---- multi-GPU feature-cache assembly (new; the reference is single-process) ------------------ */
+
+/* Fused extract + all-gather over NVLink peer memory: this rank extracts its n_local clips and the
+ * kernel epilogue stores every row into the same slot of all `world` ranks' caches
+ * (d_peer_out[r] = base of rank r's full [world*n_local, frames, cols] cache, peer-mapped).
+ * The caller owns the cross-rank barrier that follows. */
+int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
+                           int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank,
+                           void* cuda_stream);
+
+/* Plain NCCL all-gather of per-rank feature shards (baseline for the fused path).  nccl_comm is an
+ * ncclComm_t; libnccl.so.2 is resolved with dlopen at first use. */
+int scf_allgather_nccl(void* nccl_comm, const float* d_local, int64_t n_local_floats, float* d_all,
+                       void* cuda_stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+const char* scf_last_error(void);
+int scf_version(void);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches claim). */
+int64_t scf_launch_count(void);
+/* Measured FP32 FMA throughput (FLOP/s) of the plan's device: micro-benchmark for the compute
+ * roofline that MEASURED_PEAKS.json does not hold. */
+int scf_measure_fp32_flops(int32_t device, double* flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCFEAT_H */

@@ -1,0 +1,342 @@
+"""Parity of the CUDA path (through the C ABI, via the ctypes host package) against the CPU oracle and the
+committed reference fixtures.  Run on the B200 box:  python -m pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star, fp32 against the float64 reference):
+  * log features (mel_spec / bark_spec):  max |diff| <= 1e-3
+  * cepstra (mfcc_spec / bfcc_spec):      max |diff| <= 1e-4 * max |ref| per clip,
+                                          and allclose(rtol=1e-4, atol=1e-4)
+    (element-wise relative error is meaningless where |ref| ~ 1e-5)
+  * power spectrum:                       |diff| <= 1e-5 * max(ref) per frame
+"""
+import numpy as np
+import pytest
+
+import scfeat
+from oracle import bark as obark, pipeline as opipe, sonopy as osonopy
+
+pytestmark = pytest.mark.gpu
+
+LOG_TOL = 1e-3
+CEP_REL = 1e-4
+
+
+def audio_of(pcm):
+    return pcm.astype(np.float32) / 32768.0
+
+
+def assert_cepstrum_close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    scale = np.abs(want).reshape(want.shape[0], -1).max(axis=1) if want.ndim == 3 else np.abs(want).max()
+    err = np.abs(got - want)
+    if want.ndim == 3:
+        err = err.reshape(want.shape[0], -1).max(axis=1)
+        assert (err <= CEP_REL * scale).all(), (err / scale).max()
+    else:
+        assert err.max() <= CEP_REL * scale, err.max() / scale
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+
+
+def assert_log_close(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= LOG_TOL, np.abs(got - want).max()
+
+
+# ------------------------------------------------------------------ config 1: the 8 example wavs
+def test_example_wavs_mfcc_vs_oracle(example_pcm):
+    _, pcm = example_pcm
+    want = np.stack([osonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 20) for a in audio_of(pcm)])
+    # int16 PCM in, one batched call (classifier/data.py path)
+    got = scfeat.data_utils.extract_features_batch(pcm)
+    assert got.shape == (8, 30, 20, 1) and got.dtype == np.float32
+    assert_cepstrum_close(got[..., 0], want)
+    # float audio in, one call per clip (sonopy.mfcc_spec call shape, data_utils.py:69)
+    for a, w in zip(audio_of(pcm), want):
+        g = scfeat.sonopy.mfcc_spec(a, 16000, (1024, 512), num_filt=20, fft_size=1024, num_coeffs=20)
+        assert_cepstrum_close(g, w)
+
+
+def test_example_wavs_vs_compiled_reference_cpp(example_pcm, ref_cpp):
+    _, pcm = example_pcm
+    got = scfeat.data_utils.extract_features_batch(pcm)[..., 0]
+    assert_cepstrum_close(got, ref_cpp['mfcc_params_json'])        # inference/tflite/mfcc.h output
+    names, _ = example_pcm
+    r = names.index('right_1')
+    np.testing.assert_allclose(got[r, 0, :5], [-1.71329153, 1.68849206, 2.06822109, 3.96351266, 2.23058176], atol=2e-5)
+
+
+def test_example_wavs_logmel_and_power(example_pcm, ref_bark):
+    _, pcm = example_pcm
+    a = audio_of(pcm)
+    for x in a:
+        assert_log_close(scfeat.sonopy.mel_spec(x, 16000, (1024, 512), 1024, 20),
+                         osonopy.mel_spec(x, 16000, (1024, 512), 1024, 20))
+    for i in range(2):
+        got = scfeat.sonopy.power_spec(a[i], (1024, 512), 1024).astype(np.float64)
+        want = ref_bark['power_1024_512_1024'][i]
+        assert got.shape == want.shape == (30, 513)
+        assert (np.abs(got - want).max(axis=1) <= 1e-5 * want.max(axis=1)).all()
+
+
+def test_example_wavs_bark_and_bfcc_vs_reference_file(example_pcm, ref_bark):
+    _, pcm = example_pcm
+    a = audio_of(pcm)
+    for key, args in [('bfcc_1024_512_1024_20_20', (1024, 512, 1024, 20, 20)),
+                      ('bfcc_1024_512_1024_26_13', (1024, 512, 1024, 26, 13)),
+                      ('bfcc_512_256_512_26_13', (512, 256, 512, 26, 13))]:
+        got = np.stack([scfeat.bark_feature.bfcc_spec(x, 16000, *args) for x in a])
+        assert_cepstrum_close(got, ref_bark[key])
+    for key, args in [('bark_1024_512_1024_24', (1024, 512, 1024, 24)), ('bark_1024_512_1024_20', (1024, 512, 1024, 20)),
+                      ('bark_512_256_512_24', (512, 256, 512, 24))]:
+        got = np.stack([scfeat.bark_feature.bark_spec(x, 16000, *args) for x in a])
+        assert_log_close(got, ref_bark[key])
+
+
+def test_long_clip_bark_config5_shape(ref_bark):
+    lf = audio_of(ref_bark['long_pcm'])
+    assert_cepstrum_close(scfeat.bark_feature.bfcc_spec(lf, 16000, 1024, 512, 1024, 26, 13),
+                          ref_bark['long_bfcc_1024_512_1024_26_13'])
+    assert_log_close(scfeat.bark_feature.bark_spec(lf, 16000, 1024, 512, 1024, 24), ref_bark['long_bark_1024_512_1024_24'])
+    # int16 input gives the same answer as the float path
+    g16 = scfeat.bark_feature.bfcc_spec(ref_bark['long_pcm'], 16000, 1024, 512, 1024, 26, 13)
+    assert_cepstrum_close(g16, ref_bark['long_bfcc_1024_512_1024_26_13'])
+
+
+# ------------------------------------------------------------------ config 2: batch of 512 synthetic clips
+def synth_batch(kind, example):
+    rng = np.random.default_rng(0)
+    if kind == 'uniform':
+        return rng.integers(-32768, 32768, size=(512, 16000), dtype=np.int16)
+    if kind == 'gaussian':
+        return np.clip(np.round(rng.normal(0, 3000, size=(512, 16000))), -32768, 32767).astype(np.int16)
+    return np.tile(example, (64, 1))
+
+
+@pytest.mark.parametrize('kind', ['uniform', 'gaussian', 'tiled'])
+def test_batch512_vs_oracle(example_pcm, kind):
+    pcm = synth_batch(kind, example_pcm[1])
+    got = scfeat.data_utils.extract_features_batch(pcm)[..., 0]
+    assert got.shape == (512, 30, 20)
+    idx = np.arange(512) if kind != 'tiled' else np.arange(8)
+    want = np.stack([osonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 20) for a in audio_of(pcm[idx])])
+    assert_cepstrum_close(got[idx], want)
+    if kind == 'tiled':      # identical inputs -> bit-identical rows wherever they sit in the batch
+        for r in range(1, 64):
+            assert np.array_equal(got[8 * r:8 * r + 8], got[:8])
+
+
+# ------------------------------------------------------------------ edge cases the reference defines
+def test_all_zero_clip_and_short_inputs():
+    z = scfeat.sonopy.mfcc_spec(np.zeros(16000, np.float32), 16000, (1024, 512), 1024, 20, 20)
+    assert z.shape == (30, 20)
+    np.testing.assert_allclose(z[:, 0], -36.04365339, atol=1e-4)
+    assert np.abs(z[:, 1:]).max() < 1e-4
+    assert scfeat.sonopy.mfcc_spec(np.zeros(1023, np.float32), 16000, (1024, 512), 1024, 20, 20).shape == (0, 20)
+    assert scfeat.sonopy.mfcc_spec(np.zeros(1023, np.float32), 16000, (1024, 512), 1024, 20, 30).shape == (0, 20)
+    assert scfeat.bark_feature.bfcc_spec(np.zeros(10, np.float32), 16000, 1024, 512).shape == (0, 13)
+    assert scfeat.sonopy.power_spec(np.zeros(100, np.float32)).shape == (0, 257)
+    one = scfeat.sonopy.mfcc_spec(np.ones(1024, np.float32), 16000, (1024, 512), 1024, 20, 20)
+    assert one.shape == (1, 20)
+    assert_cepstrum_close(one, osonopy.mfcc_spec(np.ones(1024, np.float32), 16000, (1024, 512), 1024, 20, 20))
+
+
+def test_odd_frame_count_and_ncoeffs_gt_nfilt(example_pcm):
+    _, pcm = example_pcm
+    a = audio_of(pcm[3])[:1024 + 512 * 6]          # 7 frames: the last pair is half empty
+    want = osonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 30)
+    got = scfeat.sonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 30)
+    assert got.shape == want.shape == (7, 20)
+    assert_cepstrum_close(got, want)
+
+
+@pytest.mark.parametrize('window,hop,nfft,nf,nc', [(160, 80, 512, 20, 13), (512, 256, 512, 20, 13), (400, 160, 512, 26, 13),
+                                                   (256, 128, 256, 20, 13), (1200, 400, 1024, 20, 20),
+                                                   (1024, 300, 1024, 40, 20), (640, 320, 1024, 24, 12)])
+def test_other_geometries_vs_oracle(example_pcm, window, hop, nfft, nf, nc):
+    _, pcm = example_pcm
+    for a in audio_of(pcm[:2]):
+        want = osonopy.mfcc_spec(a, 16000, (window, hop), nfft, nf, nc)
+        got = scfeat.sonopy.mfcc_spec(a, 16000, (window, hop), nfft, nf, nc)
+        assert_cepstrum_close(got, want)
+        assert_log_close(scfeat.sonopy.mel_spec(a, 16000, (window, hop), nfft, nf),
+                         osonopy.mel_spec(a, 16000, (window, hop), nfft, nf))
+
+
+def test_sonopy_defaults(example_pcm, oracle_pin):
+    _, pcm = example_pcm
+    got = np.stack([scfeat.sonopy.mfcc_spec(a, 16000) for a in audio_of(pcm[:2])])
+    assert_cepstrum_close(got, oracle_pin['mfcc_sonopy_defaults'])
+    p, f, m, c = scfeat.sonopy.mfcc_spec(audio_of(pcm[0]), 16000, return_parts=True)
+    assert p.shape[1] == 257 and f.shape == (20, 257) and m.shape[1] == 20 and c.shape[1] == 13
+
+
+def test_audio_to_feature_crop_pad_and_ragged_batch(example_pcm):
+    _, pcm = example_pcm
+    p = opipe.Params()
+    a = audio_of(pcm[0])
+    # head crop
+    longer = np.concatenate([a, a[:5000]])
+    assert_cepstrum_close(scfeat.data_utils.audio_to_feature(longer), opipe.audio_to_feature(longer, p))
+    # front pad
+    for n in (9000, 1024, 700, 1):
+        assert_cepstrum_close(scfeat.data_utils.audio_to_feature(a[:n]), opipe.audio_to_feature(a[:n], p))
+    # ragged batch of int16 clips: per-clip lengths, pad applied by the kernel
+    lengths = np.array([16000, 9000, 12345, 1024, 1023, 1, 15999, 8000], dtype=np.int32)
+    got = scfeat.data_utils.extract_features_batch(pcm, lengths)[..., 0]
+    want = np.stack([opipe.audio_to_feature(audio_of(pcm[i][:lengths[i]]), p) for i in range(8)])
+    assert_cepstrum_close(got, want)
+    assert scfeat.data_utils.vectorize_raw(a[:1000]).shape == (0, 20)
+    assert_cepstrum_close(scfeat.data_utils.vectorize_raw(a[:5000]), opipe.vectorize_raw(a[:5000], p))
+
+
+def test_use_delta_and_changed_pr(example_pcm):
+    _, pcm = example_pcm
+    pr = scfeat.params.pr
+    a = audio_of(pcm[1])
+    try:
+        pr.__dict__.update(n_mfcc=13, n_filt=26, use_delta=True, window_t=0.032, hop_t=0.016, n_fft=512)
+        p = opipe.Params(n_mfcc=13, n_filt=26, use_delta=True, window_t=0.032, hop_t=0.016, n_fft=512)
+        got = scfeat.data_utils.audio_to_feature(a)
+        want = opipe.audio_to_feature(a, p)
+        assert got.shape == want.shape == (p.n_features, 26)
+        assert_cepstrum_close(got, want)
+    finally:
+        pr.__dict__.update(n_mfcc=20, n_filt=20, use_delta=False, window_t=0.064, hop_t=0.032, n_fft=1024)
+
+
+def test_preemphasis_and_hamming_vs_oracle(example_pcm):
+    """Optional front end of the C++ twin (mfcc.h:394-410): x[n] - 0.95 x[n-1] (x[-1] := 0), Hamming with
+    denominator window-1.  Oracle = the same two steps in float64 followed by the sonopy restatement."""
+    _, pcm = example_pcm
+    a = audio_of(pcm[2]).astype(np.float64)
+    pre = a.copy()
+    pre[1:] -= np.float32(0.95).astype(np.float64) * a[:-1]
+    W, H = 1024, 512
+    ham = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(W) / (W - 1))
+    frames = osonopy.frames_of(pre, W, H) * ham
+    spec = np.fft.rfft(frames, n=1024)
+    powers = (spec.real ** 2 + spec.imag ** 2) / 1024
+    from scipy.fftpack import dct
+    mels = osonopy.safe_log(powers @ osonopy.filterbanks(16000, 20, 513).T)
+    want = dct(mels, norm='ortho')[:, :20]
+    want[:, 0] = osonopy.safe_log(powers.sum(1))
+    plan = scfeat.get_plan(window=W, hop=H, n_fft=1024, n_filt=20, n_coeffs=20, preemph_alpha=0.95, window_fn='hamming')
+    assert_cepstrum_close(plan.extract_host(pcm[2]), want)
+    assert_cepstrum_close(plan.extract_host(audio_of(pcm[2])), want)
+
+
+def test_custom_bank_matches_builtin(example_pcm):
+    _, pcm = example_pcm
+    bank = obark.bark_filterbanks(nfilts=24, nfft=1024)
+    plan = scfeat.get_plan(n_filt=24, bank=scfeat.plan.BANK_CUSTOM, custom_bank=bank, output=scfeat.plan.OUT_LOG_BANK)
+    got = plan.extract_host(pcm[:2])
+    want = np.stack([obark.bark_spec(a, 16000, 1024, 512, 1024, 24) for a in audio_of(pcm[:2])])
+    assert_log_close(got, want)
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_properties_at_corpus_shard_size(example_pcm):
+    """config 3 per-rank shard (13,229 clips): batch-invariance, determinism and the log-domain scaling law."""
+    rng = np.random.default_rng(1000)
+    n = 13229
+    pcm = rng.integers(-16384, 16384, size=(n, 16000), dtype=np.int16)
+    pcm[:8] = example_pcm[1] // 2
+    got = scfeat.data_utils.extract_features_batch(pcm)[..., 0]
+    assert got.shape == (n, 30, 20) and np.isfinite(got).all()
+    again = scfeat.data_utils.extract_features_batch(pcm)[..., 0]
+    assert np.array_equal(got, again)                                        # deterministic
+    sel = rng.choice(n, 64, replace=False)
+    solo = scfeat.data_utils.extract_features_batch(pcm[sel])[..., 0]
+    assert np.array_equal(solo, got[sel])                                    # independent of batch position
+    want = np.stack([osonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 20) for a in audio_of(pcm[sel[:16]])])
+    assert_cepstrum_close(got[sel[:16]], want)
+    # doubling the samples adds ln 4 to every log band: c0 += ln 4, c1.. unchanged except through the DCT of a constant
+    dbl = scfeat.data_utils.extract_features_batch(pcm[:256] * 2)[..., 0]
+    np.testing.assert_allclose(dbl[:, :, 0] - got[:256, :, 0], np.log(4.0), atol=2e-5)
+    np.testing.assert_allclose(dbl[:, :, 2:], got[:256, :, 2:], atol=2e-4)
+
+
+def test_long_form_batch_config5_properties():
+    """config 5 shape (60 s clips, Bark bank, fft 1024) on a 32-clip slice: 1874 frames per clip, batch rows equal
+    single-clip rows, spot rows equal the oracle."""
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-32768, 32768, size=(32, 960000), dtype=np.int16)
+    plan = scfeat.get_plan(window=1024, hop=512, n_fft=1024, n_filt=26, n_coeffs=13, bank=scfeat.plan.BANK_BARK_REF)
+    got = plan.extract_host(pcm)
+    assert got.shape == (32, 1874, 13) and np.isfinite(got).all()
+    assert np.array_equal(plan.extract_host(pcm[5]), got[5])
+    want = obark.bfcc_spec(audio_of(pcm[7][:1024 + 512 * 99]), 16000, 1024, 512, 1024, 26, 13)
+    assert_cepstrum_close(got[7, :100], want)
+    want_tail = obark.bfcc_spec(audio_of(pcm[31][-(1024 + 512 * 9):]), 16000, 1024, 512, 1024, 26, 13)
+    assert_cepstrum_close(got[31, -10:], want_tail)
+
+
+# ------------------------------------------------------------------ device pointers + DLPack (torch is only plumbing)
+def test_device_api_and_dlpack(example_pcm):
+    import torch
+    _, pcm = example_pcm
+    plan = scfeat.get_plan()
+    d_in = torch.from_numpy(pcm).cuda()
+    d_out = torch.empty((8, 30, 20), dtype=torch.float32, device='cuda')
+    st = torch.cuda.current_stream()
+    plan.extract_device(d_in.data_ptr(), 8, 16000, d_out.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    host = plan.extract_host(pcm)
+    assert np.array_equal(d_out.cpu().numpy(), host)
+    cap = plan.extract_dlpack(d_in.data_ptr(), 8, 16000, stream=st.cuda_stream)
+    t = torch.from_dlpack(cap)
+    st.synchronize()
+    assert t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (8, 30, 20)
+    assert np.array_equal(t.cpu().numpy(), host)
+    del t, cap
+    cap2 = plan.extract_dlpack(d_in.data_ptr(), 8, 16000, stream=st.cuda_stream)
+    del cap2                                       # an unconsumed capsule frees its buffer
+    # strided clips: stride > clip_len
+    wide = torch.zeros((8, 16384), dtype=torch.int16, device='cuda')
+    wide[:, :16000] = d_in
+    plan.extract_device(wide.data_ptr(), 8, 16000, d_out.data_ptr(), clip_stride=16384, stream=st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), host)
+
+
+# ------------------------------------------------------------------ config 4: streaming
+@pytest.mark.parametrize('chunk', [1600, 1024, 512, 3000])
+def test_stream_matches_listener_oracle(example_pcm, chunk):
+    _, pcm = example_pcm
+    p = opipe.Params()
+    n_streams = 5
+    x = np.stack([np.concatenate([pcm[i], pcm[(i + 3) % 8]]) for i in range(n_streams)])
+    fs = scfeat.listener.FeatureStream(n_streams, max_chunk=4096)
+    oracles = [opipe.ListenerOracle(p) for _ in range(n_streams)]
+    for s in range(0, x.shape[1] - chunk + 1, chunk):
+        ring, new = fs.push(x[:, s:s + chunk])
+        for i, o in enumerate(oracles):
+            before = len(o.window_audio)
+            want = o.update_vectors(x[i, s:s + chunk].tobytes())[..., 0]
+            assert new[i] == (before + chunk - len(o.window_audio)) // p.hop_samples
+            scale = max(np.abs(want).max(), 1.0)
+            assert np.abs(ring[i] - want).max() <= CEP_REL * scale
+    one = scfeat.listener.Listener()
+    o = opipe.ListenerOracle(p)
+    for s in range(0, 16000 - chunk + 1, chunk):
+        got = one.update_vectors(pcm[2, s:s + chunk].tobytes())
+        want = o.update_vectors(pcm[2, s:s + chunk].tobytes())
+        assert got.shape == want.shape == (30, 20, 1)
+        assert np.abs(got - want).max() <= CEP_REL * max(np.abs(want).max(), 1.0)
+
+
+def test_stream_256_streams_config4():
+    rng = np.random.default_rng(2)
+    T = 12
+    chunks = rng.integers(-32768, 32768, size=(256, T, 1600), dtype=np.int16)
+    fs = scfeat.listener.FeatureStream(256, max_chunk=1600)
+    total = np.zeros(256, dtype=np.int64)
+    for t in range(T):
+        ring, new = fs.push(chunks[:, t])
+        total += new
+    assert (total == (T * 1600 - 1024) // 512 + 1).all()
+    for i in (0, 100, 255):
+        full = osonopy.mfcc_spec(audio_of(chunks[i].reshape(-1)), 16000, (1024, 512), 1024, 20, 20)
+        want = full[total[i] - 30:total[i]]
+        assert np.abs(ring[i] - want).max() <= CEP_REL * np.abs(want).max()

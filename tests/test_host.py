@@ -1,0 +1,131 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol include/scfeat.h
+declares, its float64 table builders equal the oracle's (and therefore the reference's), the params mirror
+derives the reference's sizes, and the product path fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import scfeat
+from oracle import bark as obark, pipeline as opipe, sonopy as osonopy
+from scfeat import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'scfeat.h')).read()
+    declared = set(re.findall(r'^(?:int|void|int32_t|int64_t|const char\*)\s+(scf_[a-z0-9_]+)\(', header, re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert _lib.lib().scf_version() == 100
+
+
+def test_config_default_is_params_json():
+    c = _lib.Config()
+    _lib.check(_lib.lib().scf_config_default(ctypes.byref(c)))
+    assert (c.sample_rate, c.window, c.hop, c.n_fft, c.n_filt, c.n_coeffs) == (16000, 1024, 512, 1024, 20, 20)
+    assert (c.bank, c.output, c.window_fn, c.preemph_alpha) == (_lib.BANK_MEL_SONOPY, _lib.OUT_CEPSTRUM, 0, 0.0)
+    assert c.pcm_scale == np.float32(1 / 32768)
+    assert _lib.lib().scf_out_cols(ctypes.byref(c)) == 20
+
+
+@pytest.mark.parametrize('n,w,h', [(16000, 1024, 512), (1023, 1024, 512), (1024, 1024, 512), (960000, 1024, 512),
+                                   (16000, 160, 80), (0, 1024, 512), (2047, 1024, 512), (2048, 1024, 512)])
+def test_num_frames_equals_chop_array(n, w, h):
+    assert _lib.num_frames(n, w, h) == len(scfeat.sonopy.chop_array(np.zeros(n), w, h)) == osonopy.n_frames(n, w, h)
+
+
+@pytest.mark.parametrize('sr,nf,nfft', [(16000, 20, 1024), (16000, 20, 512), (16000, 40, 512), (16000, 26, 1024),
+                                        (8000, 13, 256), (44100, 32, 1024), (16000, 64, 1024)])
+def test_mel_bank_equals_oracle(sr, nf, nfft):
+    got = _lib.build_bank(sample_rate=sr, n_fft=nfft, n_filt=nf, bank=_lib.BANK_MEL_SONOPY)
+    want = osonopy.filterbanks(sr, nf, nfft // 2 + 1)
+    assert np.array_equal(got != 0, want != 0)
+    np.testing.assert_allclose(got, want, rtol=1e-15, atol=0)
+    assert np.array_equal(scfeat.sonopy.filterbanks(sr, nf, nfft // 2 + 1), got)
+
+
+def test_mel_bank_equals_cpp_twin(ref_cpp):
+    got = _lib.build_bank(sample_rate=16000, n_fft=1024, n_filt=20, bank=_lib.BANK_MEL_SONOPY)
+    np.testing.assert_allclose(got, ref_cpp['bank_16000_20_1024'], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize('nf,nfft,scale', [(20, 512, 'constant'), (20, 1024, 'constant'), (24, 512, 'constant'),
+                                           (24, 1024, 'constant'), (26, 512, 'constant'), (26, 1024, 'constant'),
+                                           (22, 512, 'ascendant'), (22, 512, 'descendant')])
+def test_bark_bank_equals_reference_file(ref_bark, nf, nfft, scale):
+    got = scfeat.bark_feature.bark_filterbanks(nfilts=nf, nfft=nfft, sample_rate=16000, scale=scale)
+    want = ref_bark['bank_%d_%d_%s' % (nf, nfft, scale)]
+    assert np.array_equal(got != 0, want != 0)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(got, obark.bark_filterbanks(nfilts=nf, nfft=nfft, scale=scale), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize('nf,nc', [(20, 20), (26, 13), (20, 30), (24, 24)])
+def test_dct_equals_oracle(nf, nc):
+    np.testing.assert_allclose(_lib.build_dct(nf, nc), osonopy.dct2_ortho_matrix(nf, nc), rtol=0, atol=1e-15)
+
+
+def test_bark_scale_helpers_match_oracle():
+    f = np.array([0.0, 100.0, 1000.0, 7999.0])
+    np.testing.assert_array_equal(scfeat.bark_feature.hz2bark(f), obark.hz2bark(f))
+    np.testing.assert_array_equal(scfeat.bark_feature.bark2hz(f / 400), obark.bark2hz(f / 400))
+    np.testing.assert_array_equal(scfeat.bark_feature.fft2bark(f / 40), obark.fft2bark(f / 40))
+    np.testing.assert_array_equal(scfeat.bark_feature.bark2fft(f / 400), obark.bark2fft(f / 400))
+    assert scfeat.bark_feature.Fm(3.0, 3.0) == 1 and scfeat.bark_feature.Fm(9.0, 3.0) == 0
+
+
+def test_params_mirror(tmp_path):
+    pr = scfeat.params.pr
+    o = opipe.Params()
+    for k in ('window_samples', 'hop_samples', 'max_samples', 'buffer_samples', 'n_features', 'feature_size'):
+        assert getattr(pr, k) == getattr(o, k)
+    with pytest.raises(AttributeError):
+        pr.n_fft = 512
+    f = tmp_path / 'p.json'
+    f.write_text('{"n_mfcc": 13, "use_delta": true}')
+    try:
+        scfeat.params.inject_params(str(f))
+        assert pr.n_mfcc == 13 and pr.feature_size == 26
+    finally:
+        pr.__dict__.update(n_mfcc=20, use_delta=False)
+    assert scfeat.params.inject_params(str(tmp_path / 'missing.json')) is pr
+
+
+def test_host_helpers():
+    pcm = np.array([0, 1, -1, 32767, -32768], dtype='<i2')
+    a = scfeat.data_utils.buffer_to_audio(pcm.tobytes())
+    assert a.dtype == np.float32
+    np.testing.assert_array_equal(a, opipe.buffer_to_audio(pcm.tobytes()))
+    assert scfeat.data_utils.audio_to_buffer(a) == pcm.tobytes()
+    x = np.arange(12, dtype=np.float32).reshape(4, 3) ** 2
+    np.testing.assert_array_equal(scfeat.data_utils.add_deltas(x), opipe.add_deltas(x))
+
+
+def test_bad_config_is_rejected():
+    c, _ = _lib.make_config(n_fft=2048)
+    h = ctypes.c_void_p()
+    assert _lib.lib().scf_plan_create(ctypes.byref(c), ctypes.byref(h)) == -1
+    assert b'n_fft' in _lib.lib().scf_last_error()
+    with pytest.raises(ValueError):
+        scfeat.data_utils.vectorize_raw(np.zeros(0, np.float32))
+    with pytest.raises(ValueError):
+        scfeat.bark_feature.bark_filterbanks(nfilts=20, nfft=512, sample_rate=16000, low_freq=300)
+
+
+def test_short_audio_frame_count():
+    assert _lib.num_frames(1000, 1024, 512) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(scfeat.ScfError) as ei:
+        scfeat.sonopy.mfcc_spec(np.zeros(16000, np.float32), 16000, (1024, 512), 1024, 20, 20)
+    assert ei.value.code == -3

@@ -1,0 +1,879 @@
+// Host side of libscfeat.so: configuration, float64 table construction (bank / DCT / twiddles /
+// window exactly as the reference computes them), plan object, C ABI (include/scfeat.h).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "scfeat_dlpack.h"
+#include "scfeat_internal.h"
+
+namespace scf {
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define SCF_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(SCF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// float64 table builders (host only)
+// ---------------------------------------------------------------------------------------------
+
+// numpy.linspace(start, stop, num, endpoint=True): arange(num) * step + start, last element := stop
+static std::vector<double> linspace(double start, double stop, int num)
+{
+    std::vector<double> v(num);
+    if (num == 1) { v[0] = start; return v; }
+    const double step = (stop - start) / (double)(num - 1);
+    for (int i = 0; i < num; ++i) v[i] = (double)i * step + start;
+    v[num - 1] = stop;
+    return v;
+}
+
+// sonopy.filterbanks(sample_rate, n_filt, fft_len) -- restated from its published algorithm; C++ twin
+// inference/tflite/mfcc.h:230-264 with low=0, high=sample_rate (speech_commands.h:304-307).
+static void build_mel_sonopy(int sample_rate, int n_filt, int n_bins, std::vector<double>& bank)
+{
+    auto hz2mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };      // mfcc.h:134-138
+    auto mel2hz = [](double m) { return 700.0 * (exp(m / 1127.0) - 1.0); };    // mfcc.h:141-145
+    std::vector<double> mels = linspace(hz2mel(0.0), hz2mel((double)sample_rate), n_filt + 2);
+    std::vector<long> grid(n_filt + 2);
+    for (int i = 0; i < n_filt + 2; ++i) grid[i] = (long)(mel2hz(mels[i]) * (double)n_bins / (double)sample_rate);
+    // sonopy's correct_grid: push repeated points forward so that no filter is empty
+    {
+        long offset = 0, prev = grid[0] - 1;
+        for (int i = 0; i < n_filt + 2; ++i) {
+            const long cur = grid[i];
+            offset = std::max(0L, offset + prev + 1 - cur);
+            grid[i] = cur + offset;
+            prev = cur;
+        }
+    }
+    bank.assign((size_t)n_filt * n_bins, 0.0);
+    for (int i = 0; i < n_filt; ++i) {
+        const long l = grid[i], m = grid[i + 1], r = grid[i + 2];
+        // np.linspace(0, 1, m-l, endpoint=False)[j] = j * (1/(m-l));  np.linspace(1, 0, r-m, False)[j] = 1 + j*(-1/(r-m))
+        for (long j = l; j < m && j < n_bins; ++j) bank[(size_t)i * n_bins + j] = (double)(j - l) * (1.0 / (double)(m - l));
+        for (long j = m; j < r && j < n_bins; ++j) bank[(size_t)i * n_bins + j] = (double)(j - m) * (-1.0 / (double)(r - m)) + 1.0;
+    }
+}
+
+// common/bark_feature.py:92-136.  bark2fft / fft2bark are used with their DEFAULT nfft=512 and
+// sample_rate=16000 (bark_feature.py:112,134 pass neither) -- reproduced on purpose.
+static void build_bark_ref(int sample_rate, int n_filt, int n_bins, int scale, std::vector<double>& bank)
+{
+    const double map_nfft = 512.0, map_rate = 16000.0;
+    auto hz2bark = [](double f) { return 6.0 * asinh(f / 600.0); };             // :27-29
+    auto bark2hz = [](double b) { return 600.0 * sinh(b / 6.0); };              // :32-34
+    auto fft2bark = [&](double k) { return hz2bark((k * map_rate) / (map_nfft + 1.0)); };     // :47-49
+    auto bark2fft = [&](double b) { return (map_nfft + 1.0) * bark2hz(b) / map_rate; };       // :52-56
+    const double high = (double)sample_rate / 2.0;
+    std::vector<double> pts = linspace(hz2bark(0.0), hz2bark(high), n_filt + 4);
+    std::vector<long> bins(n_filt + 4);
+    for (int i = 0; i < n_filt + 4; ++i) bins[i] = (long)floor(bark2fft(pts[i]));
+    bank.assign((size_t)n_filt * n_bins, 0.0);
+    double c = (scale == SCF_SCALE_DESCENDANT || scale == SCF_SCALE_CONSTANT) ? 1.0 : 0.0;
+    for (int i = 0; i < n_filt; ++i) {
+        if (scale == SCF_SCALE_DESCENDANT) {
+            c -= 1.0 / n_filt;
+            c = c * (c > 0 ? 1.0 : 0.0);
+        } else if (scale == SCF_SCALE_ASCENDANT) {
+            c += 1.0 / n_filt;
+            c = c * (c < 1 ? 1.0 : 0.0) + (c > 1 ? 1.0 : 0.0);
+        }
+        const double fc = pts[i + 2];
+        for (long j = bins[i]; j < bins[i + 4] && j < n_bins; ++j) {
+            const double fb = fft2bark((double)j);
+            double v = 0.0;                                                      // Fm, :59-72
+            if (fc - 2.5 <= fb && fb <= fc - 0.5) v = pow(10.0, 2.5 * (fb - fc + 0.5));
+            else if (fc - 0.5 < fb && fb < fc + 0.5) v = 1.0;
+            else if (fc + 0.5 <= fb && fb <= fc + 1.3) v = pow(10.0, -2.5 * (fb - fc - 0.5));
+            bank[(size_t)i * n_bins + j] = fabs(c * v);
+        }
+    }
+}
+
+static int check_config(const scf_config* c)
+{
+    if (!c) return fail(SCF_ERR_INVALID, "config is NULL");
+    if (c->n_fft != 256 && c->n_fft != 512 && c->n_fft != 1024)
+        return fail(SCF_ERR_INVALID, "n_fft must be 256, 512 or 1024");
+    if (c->window < 1 || c->hop < 1) return fail(SCF_ERR_INVALID, "window and hop must be positive");
+    if (c->sample_rate < 1) return fail(SCF_ERR_INVALID, "sample_rate must be positive");
+    if (c->output < SCF_OUT_POWER || c->output > SCF_OUT_CEPSTRUM) return fail(SCF_ERR_INVALID, "bad output kind");
+    if (c->output != SCF_OUT_POWER) {
+        if (c->n_filt < 1 || c->n_filt > 64) return fail(SCF_ERR_INVALID, "n_filt must be in 1..64");
+        if (c->bank < SCF_BANK_MEL_SONOPY || c->bank > SCF_BANK_CUSTOM) return fail(SCF_ERR_INVALID, "bad bank kind");
+        if (c->bank == SCF_BANK_CUSTOM && !c->custom_bank) return fail(SCF_ERR_INVALID, "custom bank is NULL");
+    }
+    if (c->output == SCF_OUT_CEPSTRUM && c->n_coeffs < 1) return fail(SCF_ERR_INVALID, "n_coeffs must be positive");
+    if (c->window_fn < SCF_WIN_RECT || c->window_fn > SCF_WIN_HANN) return fail(SCF_ERR_INVALID, "bad window kind");
+    return SCF_OK;
+}
+
+static int build_bank(const scf_config* c, std::vector<double>& bank)
+{
+    const int n_bins = c->n_fft / 2 + 1;
+    if (c->bank == SCF_BANK_MEL_SONOPY) build_mel_sonopy(c->sample_rate, c->n_filt, n_bins, bank);
+    else if (c->bank == SCF_BANK_BARK_REF) build_bark_ref(c->sample_rate, c->n_filt, n_bins, c->bank_scale, bank);
+    else bank.assign(c->custom_bank, c->custom_bank + (size_t)c->n_filt * n_bins);
+    return SCF_OK;
+}
+
+// scipy.fftpack.dct(type 2, norm='ortho') as a matrix, inference/tflite/mfcc.h:56-66
+static void build_dct(int n_filt, int n_out, std::vector<double>& d)
+{
+    d.assign((size_t)n_filt * n_out, 0.0);
+    for (int n = 0; n < n_filt; ++n)
+        for (int k = 0; k < n_out; ++k) {
+            double v = sqrt(2.0 / n_filt) * cos(M_PI * (n + 0.5) * k / n_filt);
+            if (k == 0) v *= sqrt(0.5);
+            d[(size_t)n * n_out + k] = v;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct Workspace {          // scratch for the host-buffer entry points
+    std::mutex mu;
+    void* d_in = nullptr;
+    size_t in_bytes = 0;
+    float* d_out = nullptr;
+    size_t out_bytes = 0;
+    int32_t* d_len = nullptr;
+    size_t len_bytes = 0;
+    cudaStream_t st = nullptr;
+};
+
+}  // namespace scf
+
+struct scf_plan {
+    scf_config cfg;
+    int device = 0;
+    int num_sms = 0;
+    int radix_r = 32;
+    int n_bins = 0;
+    int out_cols = 0;
+    float power_scale_i16 = 0.f, power_scale_f32 = 0.f;
+    // device tables
+    float4* d_tw4 = nullptr;
+    float* d_win = nullptr;
+    scf::BankTask* d_tasks = nullptr;
+    int32_t* d_task_begin = nullptr;
+    float4* d_wts4_i16 = nullptr;     // weights pre-multiplied by the int16 power scale
+    float4* d_wts4_f32 = nullptr;     // ... by the float-input power scale
+    scf::QSpec* d_qspec = nullptr;
+    float* d_dct = nullptr;
+    int n_tasks = 0, n_wts4 = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
+    scf::Workspace ws;
+};
+
+struct scf_stream {
+    const scf_plan* plan = nullptr;
+    scf::StreamState s{};
+    int max_chunk = 0;
+    int16_t* d_chunk_stage = nullptr;     // for the host-buffer push
+    float* d_ring_stage = nullptr;
+};
+
+namespace scf {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& host)
+{
+    const size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+    SCF_CUDA(cudaMalloc((void**)dptr, bytes));
+    if (!host.empty()) SCF_CUDA(cudaMemcpy(*dptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SCF_OK;
+}
+
+// Turns the dense float64 bank into balanced runs for the bank phase.
+static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins, bool with_energy, int n_groups,
+                        std::vector<BankTask>& tasks, std::vector<int32_t>& task_begin, std::vector<double>& wts,
+                        std::vector<QSpec>& qspec, int& n_dst)
+{
+    struct Run { int q, k0, n4; };
+    const int n_q = n_filt + (with_energy ? 1 : 0);
+    std::vector<Run> spans;                       // one aligned span per quantity
+    int total4 = 0;
+    for (int q = 0; q < n_q; ++q) {
+        int lo = n_bins, hi = -1;
+        if (q < n_filt) {
+            for (int k = 0; k < n_bins; ++k)
+                if (bank[(size_t)q * n_bins + k] != 0.0) { lo = std::min(lo, k); hi = std::max(hi, k); }
+        } else {
+            lo = 0; hi = n_bins - 1;
+        }
+        if (hi < 0) { spans.push_back({q, 0, 0}); continue; }
+        const int k0 = lo & ~3;
+        const int n4 = (hi - k0) / 4 + 1;
+        spans.push_back({q, k0, n4});
+        total4 += n4;
+    }
+    // cap per run so that the biggest group is close to the mean
+    int cap4 = std::max(4, (total4 + n_groups - 1) / n_groups / 2);
+    std::vector<Run> runs;
+    qspec.assign(n_q, QSpec{0, 0});
+    n_dst = 0;
+    for (const Run& s : spans) {
+        qspec[s.q].dst0 = n_dst;
+        int done = 0;
+        if (s.n4 == 0) {                      // empty filter: one zero-length run so that its partial is written (0)
+            runs.push_back({s.q, 0, 0});
+            qspec[s.q].count = 1;
+            n_dst += 1;
+            continue;
+        }
+        const int pieces = (s.n4 + cap4 - 1) / cap4;
+        for (int pc = 0; pc < pieces; ++pc) {
+            const int len = (s.n4 - done + (pieces - pc) - 1) / (pieces - pc);
+            runs.push_back({s.q, s.k0 + 4 * done, len});
+            done += len;
+        }
+        qspec[s.q].count = pieces;
+        n_dst += pieces;
+    }
+    // weights, laid out run by run in dst order
+    std::vector<int> w4_of(runs.size());
+    wts.clear();
+    for (size_t r = 0; r < runs.size(); ++r) {
+        w4_of[r] = (int)(wts.size() / 4);
+        for (int i = 0; i < 4 * runs[r].n4; ++i) {
+            const int k = runs[r].k0 + i;
+            double w = 0.0;
+            if (k < n_bins) w = (runs[r].q < n_filt) ? bank[(size_t)runs[r].q * n_bins + k] : 1.0;
+            wts.push_back(w);
+        }
+    }
+    // longest-processing-time assignment of runs to groups (cost = float4 iterations + fixed overhead)
+    std::vector<size_t> order(runs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return runs[a].n4 > runs[b].n4; });
+    std::vector<std::vector<size_t>> per_group(n_groups);
+    std::vector<int> load(n_groups, 0);
+    for (size_t idx : order) {
+        int best = 0;
+        for (int g = 1; g < n_groups; ++g)
+            if (load[g] < load[best]) best = g;
+        per_group[best].push_back(idx);
+        load[best] += runs[idx].n4 + 3;
+    }
+    tasks.clear();
+    task_begin.assign(n_groups + 1, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        task_begin[g] = (int32_t)tasks.size();
+        for (size_t idx : per_group[g])
+            tasks.push_back(BankTask{runs[idx].k0, runs[idx].n4, w4_of[idx], (int32_t)idx});
+    }
+    task_begin[n_groups] = (int32_t)tasks.size();
+}
+
+static void free_plan_tables(scf_plan* p)
+{
+    cudaFree(p->d_tw4); cudaFree(p->d_win); cudaFree(p->d_tasks); cudaFree(p->d_task_begin);
+    cudaFree(p->d_wts4_i16); cudaFree(p->d_wts4_f32); cudaFree(p->d_qspec); cudaFree(p->d_dct);
+    if (p->ws.d_in) cudaFree(p->ws.d_in);
+    if (p->ws.d_out) cudaFree(p->ws.d_out);
+    if (p->ws.d_len) cudaFree(p->ws.d_len);
+    if (p->ws.st) cudaStreamDestroy(p->ws.st);
+}
+
+static int plan_create(const scf_config* cfg, scf_plan** out)
+{
+    if (!out) return fail(SCF_ERR_INVALID, "plan_out is NULL");
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(SCF_ERR_NO_DEVICE, "no CUDA device: libscfeat has no CPU fallback");
+    }
+    int dev = cfg->device;
+    if (dev < 0) SCF_CUDA(cudaGetDevice(&dev));
+    if (dev >= n_dev) return fail(SCF_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    SCF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(SCF_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100-class; libscfeat is built for sm_100a only");
+    DeviceGuard guard(dev);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+
+    scf_plan* p = new (std::nothrow) scf_plan();
+    if (!p) return fail(SCF_ERR_ALLOC, "out of host memory");
+    p->cfg = *cfg;
+    p->cfg.device = dev;
+    p->cfg.custom_bank = nullptr;
+    p->device = dev;
+    p->num_sms = prop.multiProcessorCount;
+    p->radix_r = cfg->n_fft / 32;
+    p->n_bins = cfg->n_fft / 2 + 1;
+    p->out_cols = scf_out_cols(cfg);
+    const double pcm = (cfg->pcm_scale > 0.f) ? (double)cfg->pcm_scale : 1.0 / 32768.0;
+    // the FFT stage leaves 2*X[k]; power_spec divides by n_fft (bark_feature.py:89)
+    const double ps_f32 = 1.0 / (4.0 * cfg->n_fft);
+    const double ps_i16 = pcm * pcm * ps_f32;
+    p->power_scale_f32 = (float)ps_f32;
+    p->power_scale_i16 = (float)ps_i16;
+
+    // pass-2 twiddles: lane L handles column k1 = L % R; W_N^(k1*n2), n2 = 0..31, as float4 pairs
+    {
+        const int R = p->radix_r, N = cfg->n_fft;
+        std::vector<float4> tw(16 * 32);
+        for (int jj = 0; jj < 16; ++jj)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int k1 = lane % R;
+                const double a0 = -2.0 * M_PI * (double)((k1 * (2 * jj)) % N) / N;
+                const double a1 = -2.0 * M_PI * (double)((k1 * (2 * jj + 1)) % N) / N;
+                tw[jj * 32 + lane] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+            }
+        rc = upload(&p->d_tw4, tw);
+        if (rc) { free_plan_tables(p); delete p; return rc; }
+    }
+    // analysis window over the (uncropped) window length, inference/tflite/mfcc.h:404-407
+    if (cfg->window_fn != SCF_WIN_RECT) {
+        const int w_eff = std::min(cfg->window, cfg->n_fft);
+        std::vector<float> win(w_eff);
+        for (int j = 0; j < w_eff; ++j) {
+            const double c = cos(2.0 * M_PI * j / (double)(cfg->window - 1));
+            win[j] = (float)(cfg->window_fn == SCF_WIN_HAMMING ? 0.54 - 0.46 * c : 0.5 - 0.5 * c);
+        }
+        rc = upload(&p->d_win, win);
+        if (rc) { free_plan_tables(p); delete p; return rc; }
+    }
+    if (cfg->output != SCF_OUT_POWER) {
+        std::vector<double> bank;
+        build_bank(cfg, bank);
+        const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
+        std::vector<BankTask> tasks;
+        std::vector<int32_t> tbeg;
+        std::vector<double> wts;
+        std::vector<QSpec> qspec;
+        build_tasks(bank, cfg->n_filt, p->n_bins, cep, bank_groups(p->radix_r), tasks, tbeg, wts, qspec, p->n_dst);
+        p->n_tasks = (int)tasks.size();
+        p->n_wts4 = (int)(wts.size() / 4);
+        p->n_q = (int)qspec.size();
+        p->n_filt4 = (cfg->n_filt + 3) & ~3;
+        std::vector<float4> w_i16(p->n_wts4), w_f32(p->n_wts4);
+        for (int i = 0; i < p->n_wts4; ++i) {
+            w_i16[i] = make_float4((float)(wts[4 * i] * ps_i16), (float)(wts[4 * i + 1] * ps_i16),
+                                   (float)(wts[4 * i + 2] * ps_i16), (float)(wts[4 * i + 3] * ps_i16));
+            w_f32[i] = make_float4((float)(wts[4 * i] * ps_f32), (float)(wts[4 * i + 1] * ps_f32),
+                                   (float)(wts[4 * i + 2] * ps_f32), (float)(wts[4 * i + 3] * ps_f32));
+        }
+        if ((rc = upload(&p->d_tasks, tasks)) || (rc = upload(&p->d_task_begin, tbeg)) ||
+            (rc = upload(&p->d_wts4_i16, w_i16)) || (rc = upload(&p->d_wts4_f32, w_f32)) ||
+            (rc = upload(&p->d_qspec, qspec))) {
+            free_plan_tables(p); delete p; return rc;
+        }
+        if (cep) {
+            p->n_out = std::min(cfg->n_filt, cfg->n_coeffs);
+            std::vector<double> d;
+            build_dct(cfg->n_filt, p->n_out, d);
+            std::vector<float> dt((size_t)p->n_out * p->n_filt4, 0.f);     // [c][m], zero padded
+            for (int c = 0; c < p->n_out; ++c)
+                for (int m = 0; m < cfg->n_filt; ++m) dt[(size_t)c * p->n_filt4 + m] = (float)d[(size_t)m * p->n_out + c];
+            if ((rc = upload(&p->d_dct, dt))) { free_plan_tables(p); delete p; return rc; }
+        }
+    }
+    *out = p;
+    return SCF_OK;
+}
+
+static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
+                       int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out, KParams& kp,
+                       int64_t& n_tiles, bool& fast)
+{
+    const scf_config& c = plan->cfg;
+    if (n_clips < 0 || clip_len < 0) return fail(SCF_ERR_INVALID, "negative size");
+    if (n_clips > 0 && (!d_in || clip_stride < clip_len)) return fail(SCF_ERR_INVALID, "bad input pointer / stride");
+    if (pad != SCF_PAD_FRONT_ZERO && pad != SCF_PAD_NONE) return fail(SCF_ERR_INVALID, "bad pad kind");
+    if (n_clips > 0x7fffffffLL) return fail(SCF_ERR_INVALID, "too many clips");
+    memset(&kp, 0, sizeof(kp));
+    kp.in = d_in;
+    kp.clip_stride = clip_stride;
+    kp.clip_len = clip_len;
+    kp.lengths = d_lengths;
+    kp.pad_mode = pad;
+    kp.frames_per_clip = (int32_t)scf_num_frames(clip_len, c.window, c.hop);
+    kp.pairs_per_clip = (kp.frames_per_clip + 1) / 2;
+    kp.n_pairs = n_clips * (int64_t)kp.pairs_per_clip;
+    kp.n_clips_lo = (int32_t)n_clips;
+    kp.window = c.window;
+    kp.hop = c.hop;
+    kp.w_eff = std::min(c.window, c.n_fft);
+    kp.preemph = c.preemph_alpha;
+    kp.win = plan->d_win;
+    kp.out = d_out;
+    kp.n_peers = 0;
+    kp.peer_row0 = 0;
+    kp.out_cols = plan->out_cols;
+    kp.out_kind = c.output;
+    kp.power_scale = is_f32 ? plan->power_scale_f32 : plan->power_scale_i16;
+    kp.tw4 = plan->d_tw4;
+    kp.tasks = plan->d_tasks;
+    kp.task_begin = plan->d_task_begin;
+    kp.n_tasks = plan->n_tasks;
+    kp.wts4 = is_f32 ? plan->d_wts4_f32 : plan->d_wts4_i16;
+    kp.n_wts4 = plan->n_wts4;
+    kp.qspec = plan->d_qspec;
+    kp.n_q = plan->n_q;
+    kp.n_dst = plan->n_dst;
+    kp.n_filt = c.n_filt;
+    kp.n_filt4 = plan->n_filt4;
+    kp.n_out = plan->n_out;
+    kp.dct = plan->d_dct;
+    const int ppt = pairs_per_tile(plan->radix_r);
+    n_tiles = (kp.n_pairs + ppt - 1) / ppt;
+    fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && d_lengths == nullptr && c.preemph_alpha == 0.f &&
+           c.window_fn == SCF_WIN_RECT;
+    return SCF_OK;
+}
+
+static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
+                          int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out,
+                          float* const* peers, int world, int rank, void* cuda_stream)
+{
+    if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
+    KParams kp;
+    int64_t n_tiles;
+    bool fast;
+    int rc = fill_params(plan, is_f32, d_in, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, kp, n_tiles, fast);
+    if (rc) return rc;
+    if (peers) {
+        if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(SCF_ERR_INVALID, "bad world/rank");
+        if (plan->cfg.output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "fused gather does not support power output");
+        kp.out = nullptr;
+        kp.n_peers = world;
+        for (int r = 0; r < world; ++r) {
+            if (!peers[r]) return fail(SCF_ERR_INVALID, "peer pointer is NULL");
+            kp.peer_out[r] = peers[r];
+        }
+        kp.peer_row0 = (int64_t)rank * n_clips * kp.frames_per_clip;
+    } else if (n_clips > 0 && kp.frames_per_clip > 0 && !d_out) {
+        return fail(SCF_ERR_INVALID, "output pointer is NULL");
+    }
+    if (n_tiles == 0) return SCF_OK;
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    const size_t smem = extract_smem_bytes(plan->radix_r, kp);
+    if (smem > 113 * 1024) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
+    SCF_CUDA(launch_extract(plan->radix_r, is_f32, fast, kp, n_tiles, plan->num_sms, (cudaStream_t)cuda_stream, smem));
+    return SCF_OK;
+}
+
+template <typename T>
+static int grow(T** ptr, size_t* have, size_t need)
+{
+    if (need <= *have) return SCF_OK;
+    if (*ptr) SCF_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+    SCF_CUDA(cudaMalloc((void**)ptr, need));
+    *have = need;
+    return SCF_OK;
+}
+
+static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int64_t n_clips, int64_t clip_stride,
+                        int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+{
+    if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
+    if (n_clips < 0 || clip_len < 0) return fail(SCF_ERR_INVALID, "negative size");
+    if (n_clips == 0) return SCF_OK;
+    if (!h_in || clip_stride < clip_len) return fail(SCF_ERR_INVALID, "bad input pointer / stride");
+    const int64_t fpc = scf_num_frames(clip_len, plan->cfg.window, plan->cfg.hop);
+    if (fpc == 0) return SCF_OK;
+    if (!h_out) return fail(SCF_ERR_INVALID, "output pointer is NULL");
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = const_cast<scf_plan*>(plan)->ws;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    if (!ws.st) SCF_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+    const size_t esz = is_f32 ? 4 : 2;
+    const size_t in_bytes = (size_t)((n_clips - 1) * clip_stride + clip_len) * esz;
+    const size_t out_bytes = (size_t)n_clips * fpc * plan->out_cols * sizeof(float);
+    int rc;
+    if ((rc = grow(&ws.d_in, &ws.in_bytes, in_bytes)) || (rc = grow(&ws.d_out, &ws.out_bytes, out_bytes))) return rc;
+    const int32_t* d_len = nullptr;
+    if (h_lengths) {
+        if ((rc = grow(&ws.d_len, &ws.len_bytes, (size_t)n_clips * 4))) return rc;
+        SCF_CUDA(cudaMemcpyAsync(ws.d_len, h_lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, ws.st));
+        d_len = ws.d_len;
+    }
+    SCF_CUDA(cudaMemcpyAsync(ws.d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ws.st));
+    if (pad == SCF_PAD_NONE && h_lengths)      // rows of short clips stay untouched by the kernel: make them zero
+        SCF_CUDA(cudaMemsetAsync(ws.d_out, 0, out_bytes, ws.st));
+    rc = extract_device(plan, is_f32, ws.d_in, n_clips, clip_stride, clip_len, d_len, pad, ws.d_out, nullptr, 0, 0, ws.st);
+    if (rc) return rc;
+    SCF_CUDA(cudaMemcpyAsync(h_out, ws.d_out, out_bytes, cudaMemcpyDeviceToHost, ws.st));
+    SCF_CUDA(cudaStreamSynchronize(ws.st));
+    return SCF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DLPack hand-off
+// ---------------------------------------------------------------------------------------------
+struct DlOwner {
+    DLManagedTensor mt;
+    int64_t shape[3];
+    int device;
+};
+
+static void dl_deleter(DLManagedTensor* self)
+{
+    if (!self) return;
+    DlOwner* o = static_cast<DlOwner*>(self->manager_ctx);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(o->device);
+    cudaFree(self->dl_tensor.data);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete o;
+}
+
+}  // namespace scf
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace scf;
+
+extern "C" {
+
+int scf_config_default(scf_config* cfg)
+{
+    if (!cfg) return fail(SCF_ERR_INVALID, "cfg is NULL");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->sample_rate = 16000;      // configs/params.json
+    cfg->window = 1024;            // int(16000 * 0.064 + 0.5)
+    cfg->hop = 512;                // int(16000 * 0.032 + 0.5)
+    cfg->n_fft = 1024;
+    cfg->n_filt = 20;
+    cfg->n_coeffs = 20;
+    cfg->bank = SCF_BANK_MEL_SONOPY;
+    cfg->bank_scale = SCF_SCALE_CONSTANT;
+    cfg->output = SCF_OUT_CEPSTRUM;
+    cfg->window_fn = SCF_WIN_RECT;
+    cfg->preemph_alpha = 0.f;
+    cfg->pcm_scale = 1.0f / 32768.0f;
+    cfg->device = -1;
+    return SCF_OK;
+}
+
+int64_t scf_num_frames(int64_t n_samples, int32_t window, int32_t hop)
+{
+    if (window < 1 || hop < 1 || n_samples < window) return 0;
+    return (n_samples - window) / hop + 1;
+}
+
+int32_t scf_out_cols(const scf_config* cfg)
+{
+    if (!cfg) return 0;
+    switch (cfg->output) {
+        case SCF_OUT_POWER: return cfg->n_fft / 2 + 1;
+        case SCF_OUT_LOG_BANK: return cfg->n_filt;
+        default: return std::min(cfg->n_filt, cfg->n_coeffs);
+    }
+}
+
+int scf_build_bank(const scf_config* cfg, double* bank_out)
+{
+    scf_config c;
+    if (!cfg || !bank_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    c = *cfg;
+    if (c.output == SCF_OUT_POWER) c.output = SCF_OUT_LOG_BANK;
+    int rc = check_config(&c);
+    if (rc) return rc;
+    std::vector<double> bank;
+    build_bank(&c, bank);
+    memcpy(bank_out, bank.data(), bank.size() * sizeof(double));
+    return SCF_OK;
+}
+
+int scf_build_dct(int32_t n_filt, int32_t n_coeffs, double* dct_out)
+{
+    if (n_filt < 1 || n_coeffs < 1 || !dct_out) return fail(SCF_ERR_INVALID, "bad argument");
+    std::vector<double> d;
+    build_dct(n_filt, std::min(n_filt, n_coeffs), d);
+    memcpy(dct_out, d.data(), d.size() * sizeof(double));
+    return SCF_OK;
+}
+
+int scf_plan_create(const scf_config* cfg, scf_plan** plan_out) { return plan_create(cfg, plan_out); }
+
+void scf_plan_destroy(scf_plan* plan)
+{
+    if (!plan) return;
+    DeviceGuard guard(plan->device);
+    free_plan_tables(plan);
+    delete plan;
+}
+
+int scf_plan_config(const scf_plan* plan, scf_config* cfg_out)
+{
+    if (!plan || !cfg_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    *cfg_out = plan->cfg;
+    return SCF_OK;
+}
+
+int scf_extract_i16(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride, int32_t clip_len,
+                    const int32_t* d_lengths, int32_t pad, float* d_out, void* cuda_stream)
+{
+    return extract_device(plan, false, d_pcm, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, nullptr, 0, 0,
+                          cuda_stream);
+}
+
+int scf_extract_f32(const scf_plan* plan, const float* d_audio, int64_t n_clips, int64_t clip_stride, int32_t clip_len,
+                    const int32_t* d_lengths, int32_t pad, float* d_out, void* cuda_stream)
+{
+    return extract_device(plan, true, d_audio, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, nullptr, 0, 0,
+                          cuda_stream);
+}
+
+int scf_extract_host_i16(const scf_plan* plan, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
+                         int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+{
+    return extract_host(plan, false, h_pcm, n_clips, clip_stride, clip_len, h_lengths, pad, h_out);
+}
+
+int scf_extract_host_f32(const scf_plan* plan, const float* h_audio, int64_t n_clips, int64_t clip_stride,
+                         int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+{
+    return extract_host(plan, true, h_audio, n_clips, clip_stride, clip_len, h_lengths, pad, h_out);
+}
+
+int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride,
+                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, void** dl_out, void* cuda_stream)
+{
+    if (!plan || !dl_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    *dl_out = nullptr;
+    if (n_clips < 0 || clip_len < 0) return fail(SCF_ERR_INVALID, "negative size");
+    const int64_t fpc = scf_num_frames(clip_len, plan->cfg.window, plan->cfg.hop);
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    DlOwner* o = new (std::nothrow) DlOwner();
+    if (!o) return fail(SCF_ERR_ALLOC, "out of host memory");
+    const size_t bytes = std::max<size_t>((size_t)n_clips * fpc * plan->out_cols * sizeof(float), 256);
+    float* d_out = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_out, bytes);
+    if (e != cudaSuccess) { delete o; return fail(SCF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    if (pad == SCF_PAD_NONE && d_lengths) cudaMemsetAsync(d_out, 0, bytes, (cudaStream_t)cuda_stream);
+    int rc = extract_device(plan, false, d_pcm, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, nullptr, 0, 0,
+                            cuda_stream);
+    if (rc) { cudaFree(d_out); delete o; return rc; }
+    o->device = plan->device;
+    o->shape[0] = n_clips; o->shape[1] = fpc; o->shape[2] = plan->out_cols;
+    o->mt.dl_tensor.data = d_out;
+    o->mt.dl_tensor.device.device_type = kDLCUDA;
+    o->mt.dl_tensor.device.device_id = plan->device;
+    o->mt.dl_tensor.ndim = 3;
+    o->mt.dl_tensor.dtype.code = kDLFloat;
+    o->mt.dl_tensor.dtype.bits = 32;
+    o->mt.dl_tensor.dtype.lanes = 1;
+    o->mt.dl_tensor.shape = o->shape;
+    o->mt.dl_tensor.strides = nullptr;
+    o->mt.dl_tensor.byte_offset = 0;
+    o->mt.manager_ctx = o;
+    o->mt.deleter = dl_deleter;
+    *dl_out = &o->mt;
+    return SCF_OK;
+}
+
+int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
+                           int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank, void* cuda_stream)
+{
+    if (!d_peer_out) return fail(SCF_ERR_INVALID, "peer table is NULL");
+    return extract_device(plan, false, d_pcm, n_local, clip_stride, clip_len, nullptr, SCF_PAD_FRONT_ZERO, nullptr,
+                          d_peer_out, world, rank, cuda_stream);
+}
+
+// ---- NCCL (resolved lazily; the library itself does not link against libnccl) -------------------
+int scf_allgather_nccl(void* nccl_comm, const float* d_local, int64_t n_local_floats, float* d_all, void* cuda_stream)
+{
+    typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    static allgather_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = (allgather_fn)dlsym(h, "ncclAllGather");
+    });
+    if (!fn) return fail(SCF_ERR_NCCL, "libnccl.so.2 / ncclAllGather not found");
+    if (!nccl_comm || !d_local || !d_all || n_local_floats < 0) return fail(SCF_ERR_INVALID, "bad argument");
+    const int ncclFloat32 = 7;
+    const int rc = fn(d_local, d_all, (size_t)n_local_floats, ncclFloat32, nccl_comm, (cudaStream_t)cuda_stream);
+    if (rc != 0) return fail(SCF_ERR_NCCL, "ncclAllGather failed with code " + std::to_string(rc));
+    return SCF_OK;
+}
+
+// ---- streaming --------------------------------------------------------------------------------
+int scf_stream_create(const scf_plan* plan, int32_t n_streams, int32_t ring_rows, int32_t max_chunk,
+                      scf_stream** stream_out)
+{
+    if (!plan || !stream_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    *stream_out = nullptr;
+    if (n_streams < 1 || ring_rows < 1 || max_chunk < 1) return fail(SCF_ERR_INVALID, "sizes must be positive");
+    if (plan->cfg.output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "streams need a bank or cepstrum plan");
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    scf_stream* s = new (std::nothrow) scf_stream();
+    if (!s) return fail(SCF_ERR_ALLOC, "out of host memory");
+    s->plan = plan;
+    s->max_chunk = max_chunk;
+    StreamState& st = s->s;
+    st.n_streams = n_streams;
+    st.ring_rows = ring_rows;
+    st.cols = plan->out_cols;
+    // carry < window before a push (listen.py:106 leaves len - k*hop < window), so window-1+max_chunk bounds it
+    st.carry_cap = ((plan->cfg.window - 1 + max_chunk) + 7) & ~7;
+    st.max_new = (int32_t)std::max<int64_t>(1, scf_num_frames(st.carry_cap, plan->cfg.window, plan->cfg.hop));
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&st.carry, (size_t)n_streams * st.carry_cap * 2)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&st.carry_len, (size_t)n_streams * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&st.ring, (size_t)n_streams * ring_rows * st.cols * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&st.fresh, (size_t)n_streams * st.max_new * st.cols * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&st.n_new, (size_t)n_streams * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_chunk_stage, (size_t)n_streams * max_chunk * 2)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_ring_stage, (size_t)n_streams * ring_rows * st.cols * 4)) != cudaSuccess) {
+        scf_stream_destroy(s);
+        return fail(SCF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    int rc = scf_stream_reset(s, nullptr);
+    if (rc) { scf_stream_destroy(s); return rc; }
+    cudaStreamSynchronize(nullptr);
+    *stream_out = s;
+    return SCF_OK;
+}
+
+void scf_stream_destroy(scf_stream* s)
+{
+    if (!s) return;
+    DeviceGuard guard(s->plan->device);
+    cudaFree(s->s.carry); cudaFree(s->s.carry_len); cudaFree(s->s.ring); cudaFree(s->s.fresh); cudaFree(s->s.n_new);
+    cudaFree(s->d_chunk_stage); cudaFree(s->d_ring_stage);
+    delete s;
+}
+
+int scf_stream_reset(scf_stream* s, void* cuda_stream)
+{
+    if (!s) return fail(SCF_ERR_INVALID, "stream is NULL");
+    DeviceGuard guard(s->plan->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const StreamState& x = s->s;
+    SCF_CUDA(cudaMemsetAsync(x.carry, 0, (size_t)x.n_streams * x.carry_cap * 2, st));
+    SCF_CUDA(cudaMemsetAsync(x.carry_len, 0, (size_t)x.n_streams * 4, st));
+    SCF_CUDA(cudaMemsetAsync(x.ring, 0, (size_t)x.n_streams * x.ring_rows * x.cols * 4, st));
+    SCF_CUDA(cudaMemsetAsync(x.n_new, 0, (size_t)x.n_streams * 4, st));
+    return SCF_OK;
+}
+
+int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_len, float* d_ring_out,
+                        int32_t* d_new_rows, void* cuda_stream)
+{
+    if (!s || !d_chunks) return fail(SCF_ERR_INVALID, "NULL argument");
+    if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
+    const scf_plan* plan = s->plan;
+    DeviceGuard guard(plan->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const StreamState& x = s->s;
+    SCF_CUDA(launch_stream_append(x, d_chunks, chunk_len, st));
+    int rc = extract_device(plan, false, x.carry, x.n_streams, x.carry_cap, x.carry_cap, x.carry_len, SCF_PAD_NONE,
+                            x.fresh, nullptr, 0, 0, st);
+    if (rc) return rc;
+    SCF_CUDA(launch_stream_commit(x, plan->cfg.window, plan->cfg.hop, d_ring_out, d_new_rows, st));
+    return SCF_OK;
+}
+
+int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chunk_len, float* h_ring_out,
+                             int32_t* h_new_rows)
+{
+    if (!s || !h_chunks) return fail(SCF_ERR_INVALID, "NULL argument");
+    if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
+    DeviceGuard guard(s->plan->device);
+    const StreamState& x = s->s;
+    SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)x.n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
+    int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, h_ring_out ? s->d_ring_stage : nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (h_ring_out)
+        SCF_CUDA(cudaMemcpyAsync(h_ring_out, s->d_ring_stage, (size_t)x.n_streams * x.ring_rows * x.cols * 4,
+                                 cudaMemcpyDeviceToHost, nullptr));
+    if (h_new_rows)
+        SCF_CUDA(cudaMemcpyAsync(h_new_rows, x.n_new, (size_t)x.n_streams * 4, cudaMemcpyDeviceToHost, nullptr));
+    SCF_CUDA(cudaStreamSynchronize(nullptr));
+    return SCF_OK;
+}
+
+// ---- misc -------------------------------------------------------------------------------------
+const char* scf_last_error(void) { return g_err.c_str(); }
+int scf_version(void) { return SCF_VERSION; }
+int64_t scf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int scf_measure_fp32_flops(int32_t device, double* flops_out)
+{
+    if (!flops_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(SCF_ERR_NO_DEVICE, "no CUDA device");
+    }
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    SCF_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    float* d = nullptr;
+    SCF_CUDA(cudaMalloc((void**)&d, (size_t)grid * 256 * 4));
+    cudaEvent_t e0, e1;
+    SCF_CUDA(cudaEventCreate(&e0));
+    SCF_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        SCF_CUDA(cudaEventRecord(e0, nullptr));
+        SCF_CUDA(launch_fp32_probe(d, iters, grid, nullptr));
+        SCF_CUDA(cudaEventRecord(e1, nullptr));
+        SCF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SCF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * grid * 256 / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, flops);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *flops_out = best;
+    return SCF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// Internal declarations shared by the host side (scfeat_host.cu) and the kernels
+// (scfeat_kernels.cu).  Not part of the ABI -- see include/scfeat.h for that.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scfeat.h"
+
+namespace scf {
+
+constexpr int kWarps = 8;                 // warps per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxPeers = 8;
+
+// One filterbank work item of the bank phase: a run of 4*n4 consecutive bins of one filter.
+struct BankTask {
+    int32_t k0;      // first bin (multiple of 4)
+    int32_t n4;      // number of float4 groups
+    int32_t w4;      // offset of the weights in float4 units
+    int32_t dst;     // partial-sum slot
+};
+
+// Which partial sums make up output quantity q (filter q, or the frame energy for q == n_filt).
+struct QSpec {
+    int32_t dst0;
+    int32_t count;
+};
+
+// Everything a launch needs; passed by value (fits the 4 KB parameter space easily).
+struct KParams {
+    const void* in;              // int16_t* or float*
+    int64_t clip_stride;         // elements between clips
+    int64_t n_pairs;             // n_clips * pairs_per_clip
+    int32_t n_clips_lo;          // (unused high bits guard) n_clips fits int32 for every config
+    int32_t clip_len;            // samples per (padded) clip
+    const int32_t* lengths;      // nullable
+    int32_t pad_mode;            // scf_pad_kind
+    int32_t frames_per_clip;     // rows per clip in the output
+    int32_t pairs_per_clip;      // ceil(frames_per_clip / 2)
+    int32_t window, hop, w_eff;  // w_eff = min(window, n_fft)
+    float preemph;               // 0 = off
+    const float* win;            // nullable window table [w_eff]
+    // output
+    float* out;                  // rank-local output, or NULL when peer_out is used
+    float* peer_out[kMaxPeers];  // fused all-gather targets
+    int32_t n_peers;             // 0 = plain
+    int64_t peer_row0;           // first output row of this rank inside the gathered cache
+    int32_t out_cols;
+    int32_t out_kind;            // scf_output_kind
+    float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
+    // tables (device)
+    const float4* tw4;           // [16][32] pass-2 twiddles
+    const BankTask* tasks;       // grouped by bank-phase thread group
+    const int32_t* task_begin;   // [n_groups + 1]
+    int32_t n_tasks;
+    const float4* wts4;          // bank weights, pre-multiplied by power_scale
+    int32_t n_wts4;
+    const QSpec* qspec;          // [n_q]
+    int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)
+    int32_t n_dst;               // number of partial-sum slots
+    int32_t n_filt;
+    int32_t n_filt4;             // n_filt rounded up to a multiple of 4
+    int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)
+    const float* dct;            // [n_out][n_filt4]
+};
+
+struct LaunchGeom {
+    int grid;
+    size_t smem;
+};
+
+// scfeat_kernels.cu
+cudaError_t launch_extract(int radix_r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles,
+                           int num_sms, cudaStream_t st, size_t smem_bytes);
+size_t extract_smem_bytes(int radix_r, const KParams& p);
+int pairs_per_tile(int radix_r);
+int bank_groups(int radix_r);
+cudaError_t prepare_kernels(int device);
+
+// streaming helpers (scfeat_kernels.cu)
+struct StreamState {
+    int16_t* carry;        // [n_streams][carry_cap]
+    int32_t* carry_len;    // [n_streams]
+    float* ring;           // [n_streams][ring_rows][cols]
+    float* fresh;          // [n_streams][max_new][cols]
+    int32_t* n_new;        // [n_streams]
+    int32_t n_streams, carry_cap, ring_rows, cols, max_new;
+};
+cudaError_t launch_stream_append(const StreamState& s, const int16_t* chunks, int chunk_len, cudaStream_t st);
+cudaError_t launch_stream_commit(const StreamState& s, int window, int hop, float* ring_out, int32_t* new_out,
+                                 cudaStream_t st);
+cudaError_t launch_fp32_probe(float* out, int iters, int grid, cudaStream_t st);
+
+void count_launch(int n);
+
+}  // namespace scf

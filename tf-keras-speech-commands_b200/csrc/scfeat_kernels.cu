@@ -1,0 +1,517 @@
+// sm_100a kernels of libscfeat: fused  PCM -> frames -> real FFT -> power -> filterbank -> log -> DCT.
+//
+// Replaces the arithmetic of sonopy.mfcc_spec / mel_spec / power_spec (reference call site
+// common/data_utils.py:69), common/bark_feature.py:85-175 and the C++ twin
+// inference/tflite/mfcc.h:295-456.  Design notes live in DESIGN.md; the short version:
+//
+//  * One persistent CTA (8 warps) walks "tiles" of 8*G frame PAIRS (G = 32 / R, R = n_fft / 32).
+//  * FFT stage, one warp per G pairs, no CTA-level sync:
+//      two real frames A, B are packed as z = A + iB and transformed by ONE complex n_fft-point FFT,
+//      done as R-point FFTs (pass 1, lane = n2, stride-32 samples) and 32-point FFTs (pass 2,
+//      lane = k1) entirely in registers (generated straight-line code, fft_gen.cuh), with a single
+//      shared-memory transpose in between.  The two spectra are separated with the mirror identity
+//      A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i ; only the upper half of Z
+//      goes through shared memory for that.  The factor 1/2, 1/n_fft and the PCM scale are folded
+//      into the filterbank weights.
+//  * Bank stage, CTA-wide: lanes <-> frame slots, thread groups <-> host-balanced runs of the sparse
+//    filterbank (float4 smem reads of power rows and weights), partial sums to shared memory.
+//  * Epilogue: sum partials -> log(max(., eps)) -> DCT-II (or pass-through) -> global rows; optionally
+//    the same rows are stored to every peer GPU's cache (fused all-gather over NVLink).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_gen.cuh"
+#include "scfeat_internal.h"
+
+namespace scf {
+
+#define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
+
+template <int R>
+struct Geo {
+    static constexpr int NFFT = 32 * R;
+    static constexpr int NB = 16 * R;                 // highest bin index (n_fft / 2)
+    static constexpr int LOG2R = (R == 32) ? 5 : (R == 16) ? 4 : 3;
+    static constexpr int G = 32 / R;                  // frame pairs per warp
+    static constexpr int PPT = kWarps * G;            // pairs per tile
+    static constexpr int SLOTS = 2 * PPT;             // frame slots per tile
+    static constexpr int NGRP = kThreads / SLOTS;     // bank-phase thread groups
+    static constexpr int XROW = 2 * R + 4;            // floats per exchange row (16 B pad -> conflict-free float4 rows)
+    static constexpr int XPAIR = 32 * XROW;
+    static constexpr int XWARP = G * XPAIR;           // floats of shared memory owned by one warp
+    static constexpr int MIR = 2 * NB + 4;            // floats per pair: upper half of Z (+1 slot for Z[0])
+    static constexpr int PROW = NB + 4;               // floats per power row ( = 4 mod 32 -> conflict-free float4 columns)
+    static constexpr int P_OFF = G * MIR;             // power rows start behind the mirror buffers
+    static constexpr int NLOAD = R + R / 2;           // fast path: strided samples per lane covering both frames
+    static_assert(P_OFF + 2 * G * PROW + 32 <= XWARP, "power rows must fit in the warp's exchange region");
+};
+
+__device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+
+template <int R>
+__device__ __forceinline__ void fft_r(float (&xr)[R], float (&xi)[R])
+{
+    if constexpr (R == 32) fft32_dit(xr, xi);
+    else if constexpr (R == 16) fft16_dit(xr, xi);
+    else fft8_dit(xr, xi);
+}
+
+struct ClipGeom {
+    int32_t len;        // valid samples
+    int32_t pad;        // zeros in front (SCF_PAD_FRONT_ZERO)
+    int32_t n_frames;   // rows this clip produces
+};
+
+__device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
+{
+    ClipGeom g;
+    int32_t len = p.clip_len;
+    if (p.lengths != nullptr) len = min(max(__ldg(p.lengths + clip), 0), p.clip_len);
+    g.len = len;
+    if (p.pad_mode == SCF_PAD_FRONT_ZERO) {
+        g.pad = p.clip_len - len;
+        g.n_frames = p.frames_per_clip;
+    } else {
+        g.pad = 0;
+        g.n_frames = (len >= p.window) ? (len - p.window) / p.hop + 1 : 0;
+    }
+    return g;
+}
+
+// Generic loader: any window / hop / per-clip length / pre-emphasis / window function.
+template <int R, typename InT>
+__device__ __forceinline__ void load_frame_generic(const KParams& p, const InT* __restrict__ clip_base,
+                                                   const ClipGeom& cg, int frame, int lane, float (&dst)[R])
+{
+    const bool valid = frame < cg.n_frames;
+    const int64_t s0 = (int64_t)frame * p.hop - cg.pad;     // index of sample n = 0 in the clip's own data
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int n1 = scf_bitrev(i, Geo<R>::LOG2R);
+        const int n = lane + 32 * n1;
+        float v = 0.f;
+        if (valid && n < p.w_eff) {
+            const int64_t a = s0 + n;
+            if (a >= 0 && a < cg.len) {
+                v = to_f32(__ldg(clip_base + a));
+                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(__ldg(clip_base + a - 1)), v);
+            }
+            if (p.win != nullptr) v *= __ldg(p.win + n);
+        }
+        dst[i] = v;
+    }
+}
+
+template <int R, typename InT, bool FAST>
+__global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, const int64_t n_tiles)
+{
+    using geo = Geo<R>;
+    extern __shared__ __align__(16) float smem[];
+
+    // ---- shared memory carve-up (must match extract_smem_bytes) ----------------------------------
+    float* s_xch = smem;
+    float4* s_tw4 = reinterpret_cast<float4*>(s_xch + kWarps * geo::XWARP);
+    float4* s_wts4 = s_tw4 + 16 * 32;
+    float* s_dct = reinterpret_cast<float*>(s_wts4 + p.n_wts4);
+    float* s_part = s_dct + p.n_out * p.n_filt4;
+    float* s_logq = s_part + p.n_dst * geo::SLOTS;
+    const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
+    int4* s_tasks = reinterpret_cast<int4*>(s_logq + n_lq * geo::SLOTS);
+    int32_t* s_tbeg = reinterpret_cast<int32_t*>(s_tasks + p.n_tasks);
+    int2* s_qspec = reinterpret_cast<int2*>(s_tbeg + ((geo::NGRP + 1 + 1) & ~1));
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    // ---- one-time per CTA: tables into shared memory, exchange area zeroed (its never-written pad
+    //      words are later multiplied by zero weights and must not hold NaN bit patterns) -------------
+    for (int i = tid; i < kWarps * geo::XWARP / 4; i += kThreads)
+        reinterpret_cast<float4*>(s_xch)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n_lq * geo::SLOTS; i += kThreads) s_logq[i] = 0.f;
+    for (int i = tid; i < 16 * 32; i += kThreads) s_tw4[i] = __ldg(p.tw4 + i);
+    for (int i = tid; i < p.n_wts4; i += kThreads) s_wts4[i] = __ldg(p.wts4 + i);
+    for (int i = tid; i < p.n_out * p.n_filt4; i += kThreads) s_dct[i] = __ldg(p.dct + i);
+    for (int i = tid; i < p.n_tasks; i += kThreads) s_tasks[i] = __ldg(reinterpret_cast<const int4*>(p.tasks) + i);
+    for (int i = tid; i <= geo::NGRP; i += kThreads) s_tbeg[i] = __ldg(p.task_begin + i);
+    for (int i = tid; i < p.n_q; i += kThreads) s_qspec[i] = __ldg(reinterpret_cast<const int2*>(p.qspec) + i);
+    __syncthreads();
+
+    float* xw = s_xch + warp * geo::XWARP;
+    // pass-2 role of this lane: pair g2 of the warp, column k1
+    const int g2 = lane / R;
+    const int k1 = lane % R;
+    // power rows of this warp: skewed so that the bank phase's float4 column reads are conflict-free
+    float* pw = xw + geo::P_OFF + 4 * ((2 * geo::G * warp) & 7);
+
+    // bank / epilogue role of this thread
+    const int slot = tid % geo::SLOTS;
+    const int grp = tid / geo::SLOTS;
+    const float* prow_slot;
+    {
+        const int sw = slot / (2 * geo::G);          // warp that produced this slot
+        const int ls = slot % (2 * geo::G);
+        prow_slot = s_xch + sw * geo::XWARP + geo::P_OFF + 4 * ((2 * geo::G * sw) & 7) + ls * geo::PROW;
+    }
+
+    const InT* __restrict__ in = reinterpret_cast<const InT*>(p.in);
+    const int ppc = p.pairs_per_clip;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t pair0 = tile * geo::PPT;
+
+        // =========================== FFT stage (per warp) =======================================
+        if (pair0 + warp * geo::G < p.n_pairs) {
+            // ---- pass 1: lane = n2; R-point FFT over n1 of z[n2 + 32 n1], z = A + iB ----------------
+#pragma unroll
+            for (int g = 0; g < geo::G; ++g) {
+                const int64_t gp = pair0 + warp * geo::G + g;
+                if (gp < p.n_pairs) {
+                    const int64_t clip = gp / ppc;
+                    const int q = (int)(gp - clip * ppc);
+                    const InT* __restrict__ cb = in + clip * p.clip_stride;
+                    float xr[R], xi[R];
+                    if constexpr (FAST) {
+                        // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half
+                        // their samples; lane reads x[1024q + lane + 32 j], j < R + R/2.
+                        const InT* __restrict__ src = cb + (int64_t)q * geo::NFFT + lane;
+                        const bool b_ok = (2 * q + 1) < p.frames_per_clip;
+                        float s[geo::NLOAD];
+#pragma unroll
+                        for (int j = 0; j < R; ++j) s[j] = to_f32(__ldg(src + 32 * j));
+#pragma unroll
+                        for (int j = R; j < geo::NLOAD; ++j) s[j] = b_ok ? to_f32(__ldg(src + 32 * j)) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            const int n1 = scf_bitrev(i, geo::LOG2R);
+                            xr[i] = s[n1];
+                            xi[i] = b_ok ? s[n1 + R / 2] : 0.f;
+                        }
+                    } else {
+                        const ClipGeom cg = clip_geom(p, clip);
+                        load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
+                        load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
+                    }
+                    fft_r<R>(xr, xi);
+                    float4* row = reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW);
+#pragma unroll
+                    for (int k = 0; k < R; k += 2) row[k / 2] = make_float4(xr[k], xi[k], xr[k + 1], xi[k + 1]);
+                }
+            }
+            __syncwarp();
+
+            // ---- pass 2: lane = (pair g2, column k1); twiddle, 32-point FFT over n2 -> Z[k1 + R k2] --
+            float yr[32], yi[32];
+            {
+                const float* col = xw + g2 * geo::XPAIR + 2 * k1;
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2 += 2) {
+                    const float4 t = s_tw4[(n2 / 2) * 32 + lane];
+                    const float2 a = *reinterpret_cast<const float2*>(col + n2 * geo::XROW);
+                    const float2 b = *reinterpret_cast<const float2*>(col + (n2 + 1) * geo::XROW);
+                    const int ia = scf_bitrev(n2, 5), ib = scf_bitrev(n2 + 1, 5);
+                    yr[ia] = __fmaf_rn(a.x, t.x, -a.y * t.y);
+                    yi[ia] = __fmaf_rn(a.x, t.y, a.y * t.x);
+                    yr[ib] = __fmaf_rn(b.x, t.z, -b.y * t.w);
+                    yi[ib] = __fmaf_rn(b.x, t.w, b.y * t.z);
+                }
+            }
+            __syncwarp();    // every lane has read its column: the region may now be reused
+            fft32_dit(yr, yi);
+
+            // ---- separate the two frames: upper half of Z through shared memory ---------------------
+            float2* mir = reinterpret_cast<float2*>(xw + g2 * geo::MIR);
+#pragma unroll
+            for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = make_float2(yr[k2], yi[k2]);
+            if (k1 == 0) mir[geo::NB] = make_float2(yr[0], yi[0]);       // Z[N] == Z[0]
+            __syncwarp();
+            float* pa_row = pw + (2 * g2) * geo::PROW;
+            float* pb_row = pa_row + geo::PROW;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                const int k = k1 + R * k2;
+                const float2 m = mir[geo::NB - k];                         // Z[N - k]
+                const float sr = yr[k2] + m.x, dr = yi[k2] - m.y;          // 2 A[k]
+                const float si = yi[k2] + m.y, di = m.x - yr[k2];          // 2 B[k]
+                pa_row[k] = __fmaf_rn(sr, sr, dr * dr);
+                pb_row[k] = __fmaf_rn(si, si, di * di);
+            }
+            if (k1 == 0) {                                                 // bin n_fft/2 mirrors onto itself
+                pa_row[geo::NB] = 4.f * yr[16] * yr[16];
+                pb_row[geo::NB] = 4.f * yi[16] * yi[16];
+            }
+        }
+        __syncthreads();
+
+        // =========================== where this thread's slot goes ==============================
+        int64_t out_row = -1;
+        {
+            const int64_t gp = pair0 + (slot >> 1);
+            if (gp < p.n_pairs) {
+                const int64_t clip = gp / ppc;
+                const int f = 2 * (int)(gp - clip * ppc) + (slot & 1);
+                int nfr = p.frames_per_clip;
+                if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
+                if (f < nfr) out_row = clip * p.frames_per_clip + f;
+            }
+        }
+
+        if (p.out_kind == SCF_OUT_POWER) {
+            // power_spec(): rows straight out of shared memory, coalesced along the bins
+            // warp w copies slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
+            for (int s = warp; s < geo::SLOTS; s += kWarps) {
+                const int64_t gp = pair0 + (s >> 1);
+                int64_t row = -1;
+                if (gp < p.n_pairs) {
+                    const int64_t clip = gp / ppc;
+                    const int f = 2 * (int)(gp - clip * ppc) + (s & 1);
+                    int nfr = p.frames_per_clip;
+                    if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
+                    if (f < nfr) row = clip * p.frames_per_clip + f;
+                }
+                if (row < 0) continue;
+                const int sw = s / (2 * geo::G), ls = s % (2 * geo::G);
+                const float* src = s_xch + sw * geo::XWARP + geo::P_OFF + 4 * ((2 * geo::G * sw) & 7) + ls * geo::PROW;
+                float* dst = p.out + row * p.out_cols;
+                for (int k = lane; k <= geo::NB; k += 32) dst[k] = src[k] * p.power_scale;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // =========================== bank stage ================================================
+        {
+            const int t_end = s_tbeg[grp + 1];
+            for (int t = s_tbeg[grp]; t < t_end; ++t) {
+                const int4 tk = s_tasks[t];
+                const float4* pp = reinterpret_cast<const float4*>(prow_slot + tk.x);
+                const float4* ww = s_wts4 + tk.z;
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
+                for (int i = 0; i < tk.y; ++i) {
+                    const float4 a = pp[i];
+                    const float4 w = ww[i];
+                    acc0 = __fmaf_rn(a.x, w.x, acc0);
+                    acc1 = __fmaf_rn(a.y, w.y, acc1);
+                    acc0 = __fmaf_rn(a.z, w.z, acc0);
+                    acc1 = __fmaf_rn(a.w, w.w, acc1);
+                }
+                s_part[tk.w * geo::SLOTS + slot] = acc0 + acc1;
+            }
+        }
+        __syncthreads();
+
+        // =========================== log ========================================================
+        for (int q = grp; q < p.n_q; q += geo::NGRP) {
+            const int2 qs = s_qspec[q];
+            float v = 0.f;
+            for (int j = 0; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
+            const float lv = logf(fmaxf(v, SCF_EPS));
+            if (p.out_kind == SCF_OUT_LOG_BANK) {
+                if (out_row >= 0) {
+                    if (p.n_peers == 0) {
+                        p.out[out_row * p.out_cols + q] = lv;
+                    } else {
+                        for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(p.peer_row0 + out_row) * p.out_cols + q] = lv;
+                    }
+                }
+            } else {
+                s_logq[q * geo::SLOTS + slot] = lv;
+            }
+        }
+        if (p.out_kind == SCF_OUT_LOG_BANK) continue;     // the next tile's first barrier orders s_part reuse
+        __syncthreads();
+
+        // =========================== DCT-II, c0 := log energy ===================================
+        for (int c = grp; c < p.n_out; c += geo::NGRP) {
+            float v;
+            if (c == 0) {
+                v = s_logq[p.n_filt * geo::SLOTS + slot];
+            } else {
+                const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
+                float a0 = 0.f, a1 = 0.f;
+                for (int m = 0; m < p.n_filt4; m += 4) {
+                    const float4 d = d4[m >> 2];
+                    // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
+                    a0 = __fmaf_rn(s_logq[(m + 0) * geo::SLOTS + slot], d.x, a0);
+                    a1 = __fmaf_rn(s_logq[(m + 1) * geo::SLOTS + slot], d.y, a1);
+                    a0 = __fmaf_rn(s_logq[(m + 2) * geo::SLOTS + slot], d.z, a0);
+                    a1 = __fmaf_rn(s_logq[(m + 3) * geo::SLOTS + slot], d.w, a1);
+                }
+                v = a0 + a1;
+            }
+            if (out_row >= 0) {
+                if (p.n_peers == 0) {
+                    p.out[out_row * p.out_cols + c] = v;
+                } else {
+                    for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(p.peer_row0 + out_row) * p.out_cols + c] = v;
+                }
+            }
+        }
+        // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no
+        // thread reads after the bank stage; s_part / s_logq are rewritten only behind later barriers.
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int R>
+static size_t smem_bytes_r(const KParams& p)
+{
+    using geo = Geo<R>;
+    size_t f = (size_t)kWarps * geo::XWARP + 16 * 32 * 4 + (size_t)p.n_wts4 * 4 + (size_t)p.n_out * p.n_filt4 +
+               (size_t)p.n_dst * geo::SLOTS + (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4) * geo::SLOTS;
+    size_t b = f * 4 + (size_t)p.n_tasks * 16 + (size_t)((geo::NGRP + 2) & ~1) * 4 + (size_t)p.n_q * 8;
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t extract_smem_bytes(int r, const KParams& p)
+{
+    return r == 32 ? smem_bytes_r<32>(p) : r == 16 ? smem_bytes_r<16>(p) : smem_bytes_r<8>(p);
+}
+
+int pairs_per_tile(int r) { return kWarps * (32 / r); }
+int bank_groups(int r) { return kThreads / (2 * kWarps * (32 / r)); }
+
+template <int R, typename InT, bool FAST>
+static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
+{
+    auto kern = extract_kernel<R, InT, FAST>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t grid = (int64_t)num_sms * 2;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, n_tiles);
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
+                            size_t smem)
+{
+    if (is_f32) {
+        return fast ? launch_one<R, float, true>(p, n_tiles, num_sms, st, smem)
+                    : launch_one<R, float, false>(p, n_tiles, num_sms, st, smem);
+    }
+    return fast ? launch_one<R, int16_t, true>(p, n_tiles, num_sms, st, smem)
+                : launch_one<R, int16_t, false>(p, n_tiles, num_sms, st, smem);
+}
+
+cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
+                           cudaStream_t st, size_t smem)
+{
+    switch (r) {
+        case 32: return launch_r<32>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 16: return launch_r<16>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 8: return launch_r<8>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t prepare_kernels(int) { return cudaSuccess; }
+
+// ------------------------------------------------------------------------------------------------
+// Streaming state machine of Listener.update_vectors (listen.py:96-114) for n_streams listeners.
+//   append : window_audio = concat(window_audio, chunk)                       (listen.py:101)
+//   [extract_kernel over the carry buffers, SCF_PAD_NONE, lengths = carry_len -> `fresh` rows]
+//   commit : k = frames emitted; window_audio = window_audio[k*hop:]          (listen.py:106)
+//            mfccs = concat(mfccs[k:], new_features)                          (listen.py:107-109)
+__global__ void stream_append_kernel(StreamState s, const int16_t* __restrict__ chunks, int chunk_len)
+{
+    const int st = blockIdx.x;
+    const int len = s.carry_len[st];
+    int16_t* dst = s.carry + (int64_t)st * s.carry_cap + len;
+    const int16_t* src = chunks + (int64_t)st * chunk_len;
+    for (int i = threadIdx.x; i < chunk_len; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) s.carry_len[st] = len + chunk_len;
+}
+
+__global__ void stream_commit_kernel(StreamState s, int window, int hop, float* __restrict__ ring_out,
+                                     int32_t* __restrict__ new_out)
+{
+    extern __shared__ int16_t s_keep[];
+    const int st = blockIdx.x;
+    const int len = s.carry_len[st];
+    int k = (len >= window) ? (len - window) / hop + 1 : 0;
+    const int consumed = k * hop;
+    const int keep = len - consumed;
+    int16_t* carry = s.carry + (int64_t)st * s.carry_cap;
+    // shift the carry down through shared memory (source and destination overlap)
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) s_keep[i] = carry[consumed + i];
+    // ring update: drop the k oldest rows, append the k newest of `fresh`
+    const int rows = s.ring_rows, cols = s.cols;
+    float* ring = s.ring + (int64_t)st * rows * cols;
+    const float* fresh = s.fresh + (int64_t)st * s.max_new * cols;
+    const int kk = min(k, rows);                  // listen.py:107-108 keeps only the newest `rows`
+    const int fresh0 = k - kk;
+    __syncthreads();
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) carry[i] = s_keep[i];
+    if (kk > 0) {
+        const int n_old = (rows - kk) * cols;
+        // move surviving rows up; each element is read before a later iteration could overwrite it only
+        // if processed in order, so go through registers in bounded batches
+        for (int base = 0; base < n_old; base += blockDim.x) {
+            const int i = base + threadIdx.x;
+            float v = 0.f;
+            if (i < n_old) v = ring[i + kk * cols];
+            __syncthreads();
+            if (i < n_old) ring[i] = v;
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < kk * cols; i += blockDim.x) ring[n_old + i] = fresh[fresh0 * cols + i];
+    }
+    __syncthreads();
+    if (ring_out != nullptr) {
+        float* o = ring_out + (int64_t)st * rows * cols;
+        for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) o[i] = ring[i];
+    }
+    if (threadIdx.x == 0) {
+        s.carry_len[st] = keep;
+        s.n_new[st] = k;
+        if (new_out != nullptr) new_out[st] = k;
+    }
+}
+
+cudaError_t launch_stream_append(const StreamState& s, const int16_t* chunks, int chunk_len, cudaStream_t st)
+{
+    stream_append_kernel<<<s.n_streams, 128, 0, st>>>(s, chunks, chunk_len);
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_commit(const StreamState& s, int window, int hop, float* ring_out, int32_t* new_out,
+                                 cudaStream_t st)
+{
+    stream_commit_kernel<<<s.n_streams, 128, (size_t)s.carry_cap * sizeof(int16_t), st>>>(s, window, hop, ring_out,
+                                                                                         new_out);
+    count_launch(1);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 FMA throughput probe: 8 independent FMA chains per thread, 2 flop per FMA.
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-4f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+            a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+cudaError_t launch_fp32_probe(float* out, int iters, int grid, cudaStream_t st)
+{
+    fp32_probe_kernel<<<grid, 256, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace scf

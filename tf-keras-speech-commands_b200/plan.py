@@ -1,0 +1,148 @@
+"""Plan objects: one immutable libscfeat plan per distinct feature configuration.
+
+The reference reads its configuration from the mutable module-global ``pr`` at call time
+(classifier/params.py:99-115, common/data_utils.py:69), so plans are cached BY VALUE of the
+configuration, never captured at import.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BANK_BARK_REF, BANK_CUSTOM, BANK_MEL_SONOPY, OUT_CEPSTRUM, OUT_LOG_BANK, OUT_POWER,  # noqa: F401
+                   PAD_FRONT_ZERO, PAD_NONE, ScfError, check)
+
+_cache = {}
+_cache_lock = threading.Lock()
+
+
+class Plan:
+    """Owns one ``scf_plan*``.  Thread-safe to share (the C plan is immutable)."""
+
+    def __init__(self, **kw):
+        self.cfg, self._keep = _lib.make_config(**kw)
+        self._h = ctypes.c_void_p()
+        check(_lib.lib().scf_plan_create(ctypes.byref(self.cfg), ctypes.byref(self._h)))
+        self.out_cols = int(_lib.lib().scf_out_cols(ctypes.byref(self.cfg)))
+        self.window, self.hop, self.n_fft = self.cfg.window, self.cfg.hop, self.cfg.n_fft
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            try:
+                _lib.lib().scf_plan_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def frames(self, n_samples):
+        return _lib.num_frames(n_samples, self.window, self.hop)
+
+    # ---- host numpy in -> host numpy out (what the drop-in functions use) ----------------------
+    def extract_host(self, clips, lengths=None, pad=PAD_FRONT_ZERO):
+        """clips: [n, L] (or [L]) int16 PCM or float32 audio.  Returns float32 [n, frames(L), cols]."""
+        a = np.asarray(clips)
+        single = a.ndim == 1
+        if single:
+            a = a[None, :]
+        if a.ndim != 2:
+            raise ValueError('clips must be 1-D or 2-D')
+        if a.dtype == np.int16:
+            fn = _lib.lib().scf_extract_host_i16
+        else:
+            a = a.astype(np.float32, copy=False)
+            fn = _lib.lib().scf_extract_host_f32
+        a = np.ascontiguousarray(a)
+        n, L = a.shape
+        out = np.zeros((n, self.frames(L), self.out_cols), dtype=np.float32)
+        lp = None
+        if lengths is not None:
+            lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+            if lengths.shape != (n,):
+                raise ValueError('lengths must have one entry per clip')
+            lp = lengths.ctypes.data
+        if out.size:
+            check(fn(self._h, a.ctypes.data, n, L, L, lp, pad, out.ctypes.data))
+        return out[0] if single else out
+
+    # ---- raw device pointers (torch / cupy / DLPack producers hand in .data_ptr()) -------------
+    def extract_device(self, d_in, n_clips, clip_len, d_out, clip_stride=None, d_lengths=None, pad=PAD_FRONT_ZERO,
+                       stream=0, is_f32=False):
+        fn = _lib.lib().scf_extract_f32 if is_f32 else _lib.lib().scf_extract_i16
+        check(fn(self._h, d_in, n_clips, clip_len if clip_stride is None else clip_stride, clip_len,
+                 d_lengths, pad, d_out, stream))
+
+    def extract_dlpack(self, d_in, n_clips, clip_len, clip_stride=None, d_lengths=None, pad=PAD_FRONT_ZERO, stream=0):
+        """Runs the extraction into a library-owned device buffer and returns a PyCapsule named
+        "dltensor" (consume with tf.experimental.dlpack.from_dlpack / torch.from_dlpack)."""
+        dl = ctypes.c_void_p()
+        check(_lib.lib().scf_extract_i16_dlpack(self._h, d_in, n_clips, clip_len if clip_stride is None else clip_stride,
+                                                clip_len, d_lengths, pad, ctypes.byref(dl), stream))
+        return _make_capsule(dl.value)
+
+
+# -- DLPack capsule plumbing --------------------------------------------------------------------
+class _DLManagedTensor(ctypes.Structure):
+    pass
+
+
+_DELETER = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+_DLManagedTensor._fields_ = [
+    ('data', ctypes.c_void_p), ('device_type', ctypes.c_int32), ('device_id', ctypes.c_int32),
+    ('ndim', ctypes.c_int32), ('code', ctypes.c_uint8), ('bits', ctypes.c_uint8), ('lanes', ctypes.c_uint16),
+    ('shape', ctypes.POINTER(ctypes.c_int64)), ('strides', ctypes.POINTER(ctypes.c_int64)),
+    ('byte_offset', ctypes.c_uint64), ('manager_ctx', ctypes.c_void_p), ('deleter', _DELETER),
+]
+
+_PyCapsule_Destructor = ctypes.CFUNCTYPE(None, ctypes.py_object)
+ctypes.pythonapi.PyCapsule_New.restype = ctypes.py_object
+ctypes.pythonapi.PyCapsule_New.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+ctypes.pythonapi.PyCapsule_IsValid.restype = ctypes.c_int
+ctypes.pythonapi.PyCapsule_IsValid.argtypes = [ctypes.py_object, ctypes.c_char_p]
+ctypes.pythonapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
+ctypes.pythonapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+
+@_PyCapsule_Destructor
+def _capsule_destructor(capsule):
+    # a consumer renames the capsule to "used_dltensor" and then owns the tensor; otherwise free it
+    if ctypes.pythonapi.PyCapsule_IsValid(capsule, b'dltensor'):
+        ptr = ctypes.pythonapi.PyCapsule_GetPointer(capsule, b'dltensor')
+        mt = ctypes.cast(ptr, ctypes.POINTER(_DLManagedTensor)).contents
+        if mt.deleter:
+            mt.deleter(ptr)
+
+
+def _make_capsule(ptr):
+    return ctypes.pythonapi.PyCapsule_New(ptr, b'dltensor', ctypes.cast(_capsule_destructor, ctypes.c_void_p))
+
+
+def get_plan(**kw):
+    """Plan cached by the VALUE of its configuration (custom banks are never cached)."""
+    if kw.get('custom_bank') is not None:
+        return Plan(**kw)
+    key = tuple(sorted(kw.items()))
+    with _cache_lock:
+        p = _cache.get(key)
+        if p is None:
+            p = _cache[key] = Plan(**kw)
+        return p
+
+
+def clear_plan_cache():
+    with _cache_lock:
+        _cache.clear()
+
+
+def launch_count():
+    return int(_lib.lib().scf_launch_count())
+
+
+def measure_fp32_flops(device=-1):
+    v = ctypes.c_double()
+    check(_lib.lib().scf_measure_fp32_flops(device, ctypes.byref(v)))
+    return v.value
