@@ -141,6 +141,13 @@ int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n
                            int32_t clip_len, const int32_t* d_lengths, int32_t pad, void** dl_out,
                            void* cuda_stream);
 
+/* Python-only helper: wraps a DLManagedTensor* from scf_extract_i16_dlpack in a PyCapsule named "dltensor"
+ * whose destructor calls the tensor's deleter unless a consumer took ownership (renamed it "used_dltensor").
+ * Returns a new PyObject* reference (NULL on failure).  Resolves the CPython C-API symbols from the running
+ * interpreter with dlsym, so the library does not link against libpython; call with the GIL held
+ * (ctypes.PyDLL). */
+void* scf_dlpack_make_capsule(void* dl_managed_tensor);
+
 /* ---- streaming: replaces Listener.update_vectors, listen.py:96-114 (C++ twin
  *      inference/tflite/speech_commands.h:355-449), for n_streams concurrent listeners -------- */
 

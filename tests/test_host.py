@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, 'include', 'scfeat.h')).read()
-    declared = set(re.findall(r'^(?:int|void|int32_t|int64_t|const char\*)\s+(scf_[a-z0-9_]+)\(', header, re.M))
+    declared = set(re.findall(r'^(?:int|void|void\*|int32_t|int64_t|const char\*)\s+(scf_[a-z0-9_]+)\(', header, re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
@@ -129,3 +129,43 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(scfeat.ScfError) as ei:
         scfeat.sonopy.mfcc_spec(np.zeros(16000, np.float32), 16000, (1024, 512), 1024, 20, 20)
     assert ei.value.code == -3
+
+
+def test_dlpack_capsule_plumbing_on_cpu():
+    """The capsule made by scf_dlpack_make_capsule is a valid "dltensor": torch consumes it (deleter runs when torch
+    drops the tensor) and an unconsumed capsule runs the deleter when it is garbage collected."""
+    import gc
+    import torch
+    from scfeat import plan
+
+    class DLManagedTensor(ctypes.Structure):
+        pass
+
+    DELETER = ctypes.CFUNCTYPE(None, ctypes.POINTER(DLManagedTensor))
+    DLManagedTensor._fields_ = [
+        ('data', ctypes.c_void_p), ('device_type', ctypes.c_int32), ('device_id', ctypes.c_int32),
+        ('ndim', ctypes.c_int32), ('code', ctypes.c_uint8), ('bits', ctypes.c_uint8), ('lanes', ctypes.c_uint16),
+        ('shape', ctypes.POINTER(ctypes.c_int64)), ('strides', ctypes.POINTER(ctypes.c_int64)),
+        ('byte_offset', ctypes.c_uint64), ('manager_ctx', ctypes.c_void_p), ('deleter', DELETER)]
+    deleted = []
+
+    @DELETER
+    def deleter(p):
+        deleted.append(1)
+
+    def make():
+        data = np.arange(6, dtype=np.float32)
+        shape = (ctypes.c_int64 * 2)(2, 3)
+        mt = DLManagedTensor(data.ctypes.data, 1, 0, 2, 2, 32, 1, shape, None, 0, None, deleter)
+        return plan._make_capsule(ctypes.addressof(mt)), (data, shape, mt)
+
+    cap, keep = make()
+    t = torch.from_dlpack(cap)
+    assert t.shape == (2, 3) and t.dtype == torch.float32 and t.flatten().tolist() == [0, 1, 2, 3, 4, 5]
+    del t, cap
+    gc.collect()
+    assert len(deleted) == 1            # torch owned it and released it
+    cap2, keep2 = make()
+    del cap2
+    gc.collect()
+    assert len(deleted) == 2            # nobody consumed it: the capsule destructor released it

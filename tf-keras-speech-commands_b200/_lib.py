@@ -26,7 +26,7 @@ EXPORTS = [
     'scf_config_default', 'scf_num_frames', 'scf_out_cols', 'scf_build_bank', 'scf_build_dct',
     'scf_plan_create', 'scf_plan_destroy', 'scf_plan_config',
     'scf_extract_i16', 'scf_extract_f32', 'scf_extract_host_i16', 'scf_extract_host_f32',
-    'scf_extract_i16_dlpack', 'scf_extract_i16_gather', 'scf_allgather_nccl',
+    'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_allgather_nccl',
     'scf_stream_create', 'scf_stream_destroy', 'scf_stream_reset', 'scf_stream_push_i16',
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
     'scf_measure_fp32_flops',

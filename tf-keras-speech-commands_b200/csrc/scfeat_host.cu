@@ -712,6 +712,32 @@ int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n
     return SCF_OK;
 }
 
+// ---- PyCapsule plumbing without linking libpython ----------------------------------------------
+typedef int (*py_capsule_is_valid_t)(void*, const char*);
+typedef void* (*py_capsule_get_pointer_t)(void*, const char*);
+typedef void* (*py_capsule_new_t)(void*, const char*, void (*)(void*));
+
+static void capsule_destructor(void* capsule)
+{
+    static py_capsule_is_valid_t is_valid = (py_capsule_is_valid_t)dlsym(RTLD_DEFAULT, "PyCapsule_IsValid");
+    static py_capsule_get_pointer_t get_ptr = (py_capsule_get_pointer_t)dlsym(RTLD_DEFAULT, "PyCapsule_GetPointer");
+    if (!is_valid || !get_ptr) return;
+    if (is_valid(capsule, "dltensor")) {          // not consumed: still ours to free
+        DLManagedTensor* mt = (DLManagedTensor*)get_ptr(capsule, "dltensor");
+        if (mt && mt->deleter) mt->deleter(mt);
+    }
+}
+
+void* scf_dlpack_make_capsule(void* dl_managed_tensor)
+{
+    static py_capsule_new_t cap_new = (py_capsule_new_t)dlsym(RTLD_DEFAULT, "PyCapsule_New");
+    if (!cap_new || !dl_managed_tensor) {
+        fail(SCF_ERR_INVALID, "PyCapsule_New not resolvable (not inside a Python process?) or NULL tensor");
+        return nullptr;
+    }
+    return cap_new(dl_managed_tensor, "dltensor", capsule_destructor);
+}
+
 int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
                            int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank, void* cuda_stream)
 {

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
     for (int i = tid; i < p.n_wts4; i += kThreads) s_wts4[i] = __ldg(p.wts4 + i);
     for (int i = tid; i < p.n_out * p.n_filt4; i += kThreads) s_dct[i] = __ldg(p.dct + i);
     for (int i = tid; i < p.n_tasks; i += kThreads) s_tasks[i] = __ldg(reinterpret_cast<const int4*>(p.tasks) + i);
-    for (int i = tid; i <= geo::NGRP; i += kThreads) s_tbeg[i] = __ldg(p.task_begin + i);
+    if (p.n_tasks > 0)
+        for (int i = tid; i <= geo::NGRP; i += kThreads) s_tbeg[i] = __ldg(p.task_begin + i);
     for (int i = tid; i < p.n_q; i += kThreads) s_qspec[i] = __ldg(reinterpret_cast<const int2*>(p.qspec) + i);
     __syncthreads();
 

@@ -85,40 +85,17 @@ class Plan:
         return _make_capsule(dl.value)
 
 
-# -- DLPack capsule plumbing --------------------------------------------------------------------
-class _DLManagedTensor(ctypes.Structure):
-    pass
-
-
-_DELETER = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
-_DLManagedTensor._fields_ = [
-    ('data', ctypes.c_void_p), ('device_type', ctypes.c_int32), ('device_id', ctypes.c_int32),
-    ('ndim', ctypes.c_int32), ('code', ctypes.c_uint8), ('bits', ctypes.c_uint8), ('lanes', ctypes.c_uint16),
-    ('shape', ctypes.POINTER(ctypes.c_int64)), ('strides', ctypes.POINTER(ctypes.c_int64)),
-    ('byte_offset', ctypes.c_uint64), ('manager_ctx', ctypes.c_void_p), ('deleter', _DELETER),
-]
-
-_PyCapsule_Destructor = ctypes.CFUNCTYPE(None, ctypes.py_object)
-ctypes.pythonapi.PyCapsule_New.restype = ctypes.py_object
-ctypes.pythonapi.PyCapsule_New.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
-ctypes.pythonapi.PyCapsule_IsValid.restype = ctypes.c_int
-ctypes.pythonapi.PyCapsule_IsValid.argtypes = [ctypes.py_object, ctypes.c_char_p]
-ctypes.pythonapi.PyCapsule_GetPointer.restype = ctypes.c_void_p
-ctypes.pythonapi.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
-
-
-@_PyCapsule_Destructor
-def _capsule_destructor(capsule):
-    # a consumer renames the capsule to "used_dltensor" and then owns the tensor; otherwise free it
-    if ctypes.pythonapi.PyCapsule_IsValid(capsule, b'dltensor'):
-        ptr = ctypes.pythonapi.PyCapsule_GetPointer(capsule, b'dltensor')
-        mt = ctypes.cast(ptr, ctypes.POINTER(_DLManagedTensor)).contents
-        if mt.deleter:
-            mt.deleter(ptr)
+# -- DLPack capsule plumbing: the capsule (and its destructor) is made in C, see scf_dlpack_make_capsule ----
+_pydll = None
 
 
 def _make_capsule(ptr):
-    return ctypes.pythonapi.PyCapsule_New(ptr, b'dltensor', ctypes.cast(_capsule_destructor, ctypes.c_void_p))
+    global _pydll
+    if _pydll is None:
+        _pydll = ctypes.PyDLL(_lib.LIB_PATH)          # PyDLL: keeps the GIL while PyCapsule_New runs
+        _pydll.scf_dlpack_make_capsule.restype = ctypes.py_object
+        _pydll.scf_dlpack_make_capsule.argtypes = [ctypes.c_void_p]
+    return _pydll.scf_dlpack_make_capsule(ptr)
 
 
 def get_plan(**kw):
