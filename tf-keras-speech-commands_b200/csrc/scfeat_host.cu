@@ -177,16 +177,12 @@ struct scf_plan {
     int n_bins = 0;
     int out_cols = 0;
     float power_scale_i16 = 0.f, power_scale_f32 = 0.f;
-    // device tables
-    float4* d_tw4 = nullptr;
+    // device tables: the blob the kernel copies into shared memory (one per input scale), window table
     float* d_win = nullptr;
-    scf::BankTask* d_tasks = nullptr;
-    int32_t* d_task_begin = nullptr;
-    float4* d_wts4_i16 = nullptr;     // weights pre-multiplied by the int16 power scale
-    float4* d_wts4_f32 = nullptr;     // ... by the float-input power scale
-    scf::QSpec* d_qspec = nullptr;
-    float* d_dct = nullptr;
-    int n_tasks = 0, n_wts4 = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
+    unsigned char* d_tab_i16 = nullptr;   // bank weights pre-multiplied by the int16 power scale
+    unsigned char* d_tab_f32 = nullptr;   // ... by the float-input power scale
+    int table_bytes = 0, off_wts = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
+    int n_tasks = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
     scf::Workspace ws;
 };
 
@@ -220,15 +216,26 @@ static int upload(T** dptr, const std::vector<T>& host)
     return SCF_OK;
 }
 
-// Turns the dense float64 bank into balanced runs for the bank phase.
+// Turns the dense float64 bank into the bank phase's work list: every quantity (filter, or the frame
+// energy) is cut into tasks of kTaskBins consecutive bins; consecutive tasks form runs; runs are spread over
+// the thread groups (longest-processing-time first) so that every group has about the same number of tasks.
+struct TaskList {
+    std::vector<uint32_t> words;        // grouped task words (see scfeat_internal.h)
+    std::vector<int32_t> begin;         // [n_groups + 1]
+    std::vector<double> weights;        // kTaskBins doubles per task, same order as `words`
+    std::vector<QSpec> qspec;           // per quantity: its runs' partial-sum slots
+    int n_dst = 0;
+};
+
 static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins, bool with_energy, int n_groups,
-                        std::vector<BankTask>& tasks, std::vector<int32_t>& task_begin, std::vector<double>& wts,
-                        std::vector<QSpec>& qspec, int& n_dst)
+                        TaskList& tl)
 {
-    struct Run { int q, k0, n4; };
+    struct Task { int q, k0; };
+    struct Run { int q; std::vector<Task> tasks; };
     const int n_q = n_filt + (with_energy ? 1 : 0);
-    std::vector<Run> spans;                       // one aligned span per quantity
-    int total4 = 0;
+    const int row_end = ((n_bins - 1) + 4);            // power rows hold n_fft/2 + 4 floats
+    std::vector<std::vector<Task>> per_q(n_q);
+    int total = 0;
     for (int q = 0; q < n_q; ++q) {
         int lo = n_bins, hi = -1;
         if (q < n_filt) {
@@ -237,51 +244,33 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
         } else {
             lo = 0; hi = n_bins - 1;
         }
-        if (hi < 0) { spans.push_back({q, 0, 0}); continue; }
-        const int k0 = lo & ~3;
-        const int n4 = (hi - k0) / 4 + 1;
-        spans.push_back({q, k0, n4});
-        total4 += n4;
+        if (hi < 0) { lo = 0; hi = 0; }                 // empty filter: one all-zero task so that its sum is written
+        for (int k0 = lo & ~3; k0 <= hi; k0 += kTaskBins) per_q[q].push_back({q, std::min(k0, row_end - kTaskBins)});
+        total += (int)per_q[q].size();
     }
-    // cap per run so that the biggest group is close to the mean
-    int cap4 = std::max(4, (total4 + n_groups - 1) / n_groups / 2);
+    const int cap = std::max(1, (total + n_groups - 1) / n_groups);      // tasks per run at most
     std::vector<Run> runs;
-    qspec.assign(n_q, QSpec{0, 0});
-    n_dst = 0;
-    for (const Run& s : spans) {
-        qspec[s.q].dst0 = n_dst;
+    tl.qspec.assign(n_q, QSpec{0, 0});
+    for (int q = 0; q < n_q; ++q) {
+        const int n = (int)per_q[q].size();
+        const int pieces = (n + cap - 1) / cap;
+        tl.qspec[q].dst0 = (int)runs.size();
+        tl.qspec[q].count = pieces;
         int done = 0;
-        if (s.n4 == 0) {                      // empty filter: one zero-length run so that its partial is written (0)
-            runs.push_back({s.q, 0, 0});
-            qspec[s.q].count = 1;
-            n_dst += 1;
-            continue;
-        }
-        const int pieces = (s.n4 + cap4 - 1) / cap4;
         for (int pc = 0; pc < pieces; ++pc) {
-            const int len = (s.n4 - done + (pieces - pc) - 1) / (pieces - pc);
-            runs.push_back({s.q, s.k0 + 4 * done, len});
+            const int len = (n - done + (pieces - pc) - 1) / (pieces - pc);
+            Run r;
+            r.q = q;
+            r.tasks.assign(per_q[q].begin() + done, per_q[q].begin() + done + len);
+            runs.push_back(r);
             done += len;
         }
-        qspec[s.q].count = pieces;
-        n_dst += pieces;
     }
-    // weights, laid out run by run in dst order
-    std::vector<int> w4_of(runs.size());
-    wts.clear();
-    for (size_t r = 0; r < runs.size(); ++r) {
-        w4_of[r] = (int)(wts.size() / 4);
-        for (int i = 0; i < 4 * runs[r].n4; ++i) {
-            const int k = runs[r].k0 + i;
-            double w = 0.0;
-            if (k < n_bins) w = (runs[r].q < n_filt) ? bank[(size_t)runs[r].q * n_bins + k] : 1.0;
-            wts.push_back(w);
-        }
-    }
-    // longest-processing-time assignment of runs to groups (cost = float4 iterations + fixed overhead)
+    tl.n_dst = (int)runs.size();
     std::vector<size_t> order(runs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return runs[a].n4 > runs[b].n4; });
+    std::stable_sort(order.begin(), order.end(),
+                     [&](size_t a, size_t b) { return runs[a].tasks.size() > runs[b].tasks.size(); });
     std::vector<std::vector<size_t>> per_group(n_groups);
     std::vector<int> load(n_groups, 0);
     for (size_t idx : order) {
@@ -289,22 +278,61 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
         for (int g = 1; g < n_groups; ++g)
             if (load[g] < load[best]) best = g;
         per_group[best].push_back(idx);
-        load[best] += runs[idx].n4 + 3;
+        load[best] += (int)runs[idx].tasks.size();
     }
-    tasks.clear();
-    task_begin.assign(n_groups + 1, 0);
+    // a bin may be covered by two tasks of the same quantity only where the last task was pulled back to stay
+    // inside the row; `covered` makes sure its weight is applied once
+    tl.words.clear();
+    tl.weights.clear();
+    tl.begin.assign(n_groups + 1, 0);
+    std::vector<std::vector<char>> covered(n_q, std::vector<char>(row_end, 0));
+    // weights must be decided in quantity order (not group order) so that "first task wins" is well defined
+    std::vector<std::vector<std::vector<double>>> w_of(runs.size());
+    for (size_t r = 0; r < runs.size(); ++r) {
+        w_of[r].resize(runs[r].tasks.size());
+        for (size_t t = 0; t < runs[r].tasks.size(); ++t) {
+            const Task& tk = runs[r].tasks[t];
+            std::vector<double>& w = w_of[r][t];
+            w.assign(kTaskBins, 0.0);
+            for (int i = 0; i < kTaskBins; ++i) {
+                const int k = tk.k0 + i;
+                if (k >= n_bins || covered[tk.q][k]) continue;
+                covered[tk.q][k] = 1;
+                w[i] = (tk.q < n_filt) ? bank[(size_t)tk.q * n_bins + k] : 1.0;
+            }
+        }
+    }
     for (int g = 0; g < n_groups; ++g) {
-        task_begin[g] = (int32_t)tasks.size();
-        for (size_t idx : per_group[g])
-            tasks.push_back(BankTask{runs[idx].k0, runs[idx].n4, w4_of[idx], (int32_t)idx});
+        tl.begin[g] = (int32_t)tl.words.size();
+        for (size_t r : per_group[g])
+            for (size_t t = 0; t < runs[r].tasks.size(); ++t) {
+                uint32_t word = (uint32_t)runs[r].tasks[t].k0 | ((uint32_t)r << 12);
+                if (t + 1 == runs[r].tasks.size()) word |= 0x80000000u;
+                tl.words.push_back(word);
+                tl.weights.insert(tl.weights.end(), w_of[r][t].begin(), w_of[r][t].end());
+            }
     }
-    task_begin[n_groups] = (int32_t)tasks.size();
+    tl.begin[n_groups] = (int32_t)tl.words.size();
+}
+
+// Hacker's Delight unsigned division by an invariant (round-up method); magic == 0 marks a power of two.
+static void magic_div(uint32_t d, uint32_t& magic, uint32_t& shift)
+{
+    if ((d & (d - 1)) == 0) {
+        magic = 0;
+        shift = 0;
+        while ((1u << shift) < d) ++shift;
+        return;
+    }
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;                                        // 2^(s-1) < d < 2^s
+    magic = (uint32_t)((((1ull << s) - d) << 32) / d + 1);
+    shift = s - 1;
 }
 
 static void free_plan_tables(scf_plan* p)
 {
-    cudaFree(p->d_tw4); cudaFree(p->d_win); cudaFree(p->d_tasks); cudaFree(p->d_task_begin);
-    cudaFree(p->d_wts4_i16); cudaFree(p->d_wts4_f32); cudaFree(p->d_qspec); cudaFree(p->d_dct);
+    cudaFree(p->d_win); cudaFree(p->d_tab_i16); cudaFree(p->d_tab_f32);
     if (p->ws.d_in) cudaFree(p->ws.d_in);
     if (p->ws.d_out) cudaFree(p->ws.d_out);
     if (p->ws.d_len) cudaFree(p->ws.d_len);
@@ -349,20 +377,6 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     p->power_scale_f32 = (float)ps_f32;
     p->power_scale_i16 = (float)ps_i16;
 
-    // pass-2 twiddles: lane L handles column k1 = L % R; W_N^(k1*n2), n2 = 0..31, as float4 pairs
-    {
-        const int R = p->radix_r, N = cfg->n_fft;
-        std::vector<float4> tw(16 * 32);
-        for (int jj = 0; jj < 16; ++jj)
-            for (int lane = 0; lane < 32; ++lane) {
-                const int k1 = lane % R;
-                const double a0 = -2.0 * M_PI * (double)((k1 * (2 * jj)) % N) / N;
-                const double a1 = -2.0 * M_PI * (double)((k1 * (2 * jj + 1)) % N) / N;
-                tw[jj * 32 + lane] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
-            }
-        rc = upload(&p->d_tw4, tw);
-        if (rc) { free_plan_tables(p); delete p; return rc; }
-    }
     // analysis window over the (uncropped) window length, inference/tflite/mfcc.h:404-407
     if (cfg->window_fn != SCF_WIN_RECT) {
         const int w_eff = std::min(cfg->window, cfg->n_fft);
@@ -374,40 +388,58 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         rc = upload(&p->d_win, win);
         if (rc) { free_plan_tables(p); delete p; return rc; }
     }
+    // ---- the table blob -------------------------------------------------------------------------------
+    TaskList tl;
+    std::vector<float> dct_t;
     if (cfg->output != SCF_OUT_POWER) {
         std::vector<double> bank;
         build_bank(cfg, bank);
         const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
-        std::vector<BankTask> tasks;
-        std::vector<int32_t> tbeg;
-        std::vector<double> wts;
-        std::vector<QSpec> qspec;
-        build_tasks(bank, cfg->n_filt, p->n_bins, cep, bank_groups(p->radix_r), tasks, tbeg, wts, qspec, p->n_dst);
-        p->n_tasks = (int)tasks.size();
-        p->n_wts4 = (int)(wts.size() / 4);
-        p->n_q = (int)qspec.size();
+        build_tasks(bank, cfg->n_filt, p->n_bins, cep, bank_groups(p->radix_r), tl);
+        p->n_tasks = (int)tl.words.size();
+        p->n_q = (int)tl.qspec.size();
+        p->n_dst = tl.n_dst;
         p->n_filt4 = (cfg->n_filt + 3) & ~3;
-        std::vector<float4> w_i16(p->n_wts4), w_f32(p->n_wts4);
-        for (int i = 0; i < p->n_wts4; ++i) {
-            w_i16[i] = make_float4((float)(wts[4 * i] * ps_i16), (float)(wts[4 * i + 1] * ps_i16),
-                                   (float)(wts[4 * i + 2] * ps_i16), (float)(wts[4 * i + 3] * ps_i16));
-            w_f32[i] = make_float4((float)(wts[4 * i] * ps_f32), (float)(wts[4 * i + 1] * ps_f32),
-                                   (float)(wts[4 * i + 2] * ps_f32), (float)(wts[4 * i + 3] * ps_f32));
-        }
-        if ((rc = upload(&p->d_tasks, tasks)) || (rc = upload(&p->d_task_begin, tbeg)) ||
-            (rc = upload(&p->d_wts4_i16, w_i16)) || (rc = upload(&p->d_wts4_f32, w_f32)) ||
-            (rc = upload(&p->d_qspec, qspec))) {
-            free_plan_tables(p); delete p; return rc;
-        }
         if (cep) {
             p->n_out = std::min(cfg->n_filt, cfg->n_coeffs);
             std::vector<double> d;
             build_dct(cfg->n_filt, p->n_out, d);
-            std::vector<float> dt((size_t)p->n_out * p->n_filt4, 0.f);     // [c][m], zero padded
+            dct_t.assign((size_t)p->n_out * p->n_filt4, 0.f);             // [c][m], zero padded
             for (int c = 0; c < p->n_out; ++c)
-                for (int m = 0; m < cfg->n_filt; ++m) dt[(size_t)c * p->n_filt4 + m] = (float)d[(size_t)m * p->n_out + c];
-            if ((rc = upload(&p->d_dct, dt))) { free_plan_tables(p); delete p; return rc; }
+                for (int m = 0; m < cfg->n_filt; ++m) dct_t[(size_t)c * p->n_filt4 + m] = (float)d[(size_t)m * p->n_out + c];
         }
+    }
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t sz_tw = 16 * 32 * sizeof(float4);
+    p->off_wts = (int)sz_tw;
+    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
+    p->off_tasks = (int)align16(p->off_dct + dct_t.size() * 4);
+    p->off_tbeg = (int)align16(p->off_tasks + (size_t)p->n_tasks * 4);
+    p->off_qspec = (int)align16(p->off_tbeg + tl.begin.size() * 4);
+    p->table_bytes = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
+    for (int variant = 0; variant < 2; ++variant) {
+        const double ps = variant == 0 ? ps_i16 : ps_f32;
+        std::vector<unsigned char> blob(p->table_bytes, 0);
+        // pass-2 twiddles: lane L handles column k1 = L % R; W_N^(k1*n2), n2 = 0..31, as float4 pairs
+        {
+            const int R = p->radix_r, N = cfg->n_fft;
+            float4* tw = reinterpret_cast<float4*>(blob.data());
+            for (int jj = 0; jj < 16; ++jj)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int k1 = lane % R;
+                    const double a0 = -2.0 * M_PI * (double)((k1 * (2 * jj)) % N) / N;
+                    const double a1 = -2.0 * M_PI * (double)((k1 * (2 * jj + 1)) % N) / N;
+                    tw[jj * 32 + lane] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+                }
+        }
+        float* w = reinterpret_cast<float*>(blob.data() + p->off_wts);
+        for (size_t i = 0; i < tl.weights.size(); ++i) w[i] = (float)(tl.weights[i] * ps);
+        if (!dct_t.empty()) memcpy(blob.data() + p->off_dct, dct_t.data(), dct_t.size() * 4);
+        if (!tl.words.empty()) memcpy(blob.data() + p->off_tasks, tl.words.data(), tl.words.size() * 4);
+        if (!tl.begin.empty()) memcpy(blob.data() + p->off_tbeg, tl.begin.data(), tl.begin.size() * 4);
+        if (!tl.qspec.empty()) memcpy(blob.data() + p->off_qspec, tl.qspec.data(), tl.qspec.size() * sizeof(QSpec));
+        rc = upload(variant == 0 ? &p->d_tab_i16 : &p->d_tab_f32, blob);
+        if (rc) { free_plan_tables(p); delete p; return rc; }
     }
     *out = p;
     return SCF_OK;
@@ -443,19 +475,20 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.out_cols = plan->out_cols;
     kp.out_kind = c.output;
     kp.power_scale = is_f32 ? plan->power_scale_f32 : plan->power_scale_i16;
-    kp.tw4 = plan->d_tw4;
-    kp.tasks = plan->d_tasks;
-    kp.task_begin = plan->d_task_begin;
+    kp.tables = is_f32 ? plan->d_tab_f32 : plan->d_tab_i16;
+    kp.table_bytes = plan->table_bytes;
+    kp.off_wts = plan->off_wts;
+    kp.off_dct = plan->off_dct;
+    kp.off_tasks = plan->off_tasks;
+    kp.off_tbeg = plan->off_tbeg;
+    kp.off_qspec = plan->off_qspec;
     kp.n_tasks = plan->n_tasks;
-    kp.wts4 = is_f32 ? plan->d_wts4_f32 : plan->d_wts4_i16;
-    kp.n_wts4 = plan->n_wts4;
-    kp.qspec = plan->d_qspec;
     kp.n_q = plan->n_q;
     kp.n_dst = plan->n_dst;
     kp.n_filt = c.n_filt;
     kp.n_filt4 = plan->n_filt4;
     kp.n_out = plan->n_out;
-    kp.dct = plan->d_dct;
+    magic_div((uint32_t)std::max(1, kp.pairs_per_clip), kp.ppc_magic, kp.ppc_shift);
     const int ppt = pairs_per_tile(plan->radix_r);
     n_tiles = (kp.n_pairs + ppt - 1) / ppt;
     fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && d_lengths == nullptr && c.preemph_alpha == 0.f &&
@@ -491,7 +524,22 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
     if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
     const size_t smem = extract_smem_bytes(plan->radix_r, kp);
     if (smem > 113 * 1024) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
-    SCF_CUDA(launch_extract(plan->radix_r, is_f32, fast, kp, n_tiles, plan->num_sms, (cudaStream_t)cuda_stream, smem));
+    // the kernel indexes pairs with 32 bits: very large jobs go out as several launches
+    const int ppt = pairs_per_tile(plan->radix_r);
+    const int64_t max_clips = std::max<int64_t>(1, (0x7fffffffLL - ppt) / std::max(1, kp.pairs_per_clip));
+    const size_t esz = is_f32 ? 4 : 2;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += max_clips) {
+        const int64_t nc = std::min(max_clips, n_clips - c0);
+        KParams k = kp;
+        k.in = static_cast<const unsigned char*>(d_in) + (size_t)c0 * clip_stride * esz;
+        if (d_lengths) k.lengths = d_lengths + c0;
+        const int64_t row0 = c0 * kp.frames_per_clip;
+        if (k.out) k.out = d_out + row0 * kp.out_cols;
+        k.peer_row0 = kp.peer_row0 + row0;
+        k.n_pairs = nc * (int64_t)kp.pairs_per_clip;
+        const int64_t tiles = (k.n_pairs + ppt - 1) / ppt;
+        SCF_CUDA(launch_extract(plan->radix_r, is_f32, fast, k, tiles, plan->num_sms, (cudaStream_t)cuda_stream, smem));
+    }
     return SCF_OK;
 }
 

@@ -13,13 +13,12 @@ constexpr int kWarps = 8;                 // warps per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxPeers = 8;
 
-// One filterbank work item of the bank phase: a run of 4*n4 consecutive bins of one filter.
-struct BankTask {
-    int32_t k0;      // first bin (multiple of 4)
-    int32_t n4;      // number of float4 groups
-    int32_t w4;      // offset of the weights in float4 units
-    int32_t dst;     // partial-sum slot
-};
+// Bank-phase task word: a run of exactly 16 consecutive bins (4 float4) of one filter.
+//   bits  0..11  first bin (multiple of 4)
+//   bits 12..23  partial-sum slot the run is stored to
+//   bit  31      last task of its run: store the accumulated sum
+// The 16 weights of task t sit at float4 index 4*t of the weight table (same order as the tasks).
+constexpr int kTaskBins = 16;
 
 // Which partial sums make up output quantity q (filter q, or the frame energy for q == n_filt).
 struct QSpec {
@@ -49,20 +48,19 @@ struct KParams {
     int32_t out_cols;
     int32_t out_kind;            // scf_output_kind
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
-    // tables (device)
-    const float4* tw4;           // [16][32] pass-2 twiddles
-    const BankTask* tasks;       // grouped by bank-phase thread group
-    const int32_t* task_begin;   // [n_groups + 1]
+    // tables: one device blob, copied verbatim into shared memory by a single TMA bulk copy
+    //   [twiddles float4[16][32]] [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]
+    //   [tasks u32[n_tasks]] [task_begin i32[n_groups+1]] [qspec int2[n_q]]      (every section 16-byte aligned)
+    const void* tables;
+    int32_t table_bytes;
+    int32_t off_wts, off_dct, off_tasks, off_tbeg, off_qspec;
     int32_t n_tasks;
-    const float4* wts4;          // bank weights, pre-multiplied by power_scale
-    int32_t n_wts4;
-    const QSpec* qspec;          // [n_q]
     int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)
     int32_t n_dst;               // number of partial-sum slots
     int32_t n_filt;
     int32_t n_filt4;             // n_filt rounded up to a multiple of 4
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)
-    const float* dct;            // [n_out][n_filt4]
+    uint32_t ppc_magic, ppc_shift;   // fast division by pairs_per_clip
 };
 
 struct LaunchGeom {

@@ -103,43 +103,87 @@ __device__ __forceinline__ void load_frame_generic(const KParams& p, const InT* 
     }
 }
 
+// ---- small PTX helpers: mbarrier + TMA 1-D bulk copy (tables -> shared memory) -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// n / d for the plan's pairs_per_clip with a precomputed magic (Hacker's Delight, unsigned round-up method)
+// (magic == 0 marks a power-of-two divisor: plain shift)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_t shift)
+{
+    if (magic == 0) return n >> shift;
+    const uint32_t t = __umulhi(n, magic);
+    return (t + ((n - t) >> 1)) >> shift;
+}
+
 template <int R, typename InT, bool FAST>
-__global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, const int64_t n_tiles)
+__global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, const uint32_t n_tiles)
 {
     using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
 
-    // ---- shared memory carve-up (must match extract_smem_bytes) ----------------------------------
+    // ---- shared memory carve-up (must match extract_smem_bytes; the table part mirrors the plan's blob) ----
     float* s_xch = smem;
-    float4* s_tw4 = reinterpret_cast<float4*>(s_xch + kWarps * geo::XWARP);
-    float4* s_wts4 = s_tw4 + 16 * 32;
-    float* s_dct = reinterpret_cast<float*>(s_wts4 + p.n_wts4);
-    float* s_part = s_dct + p.n_out * p.n_filt4;
+    unsigned char* s_tab = reinterpret_cast<unsigned char*>(s_xch + kWarps * geo::XWARP);
+    const float4* s_tw4 = reinterpret_cast<const float4*>(s_tab);
+    const float4* s_wts4 = reinterpret_cast<const float4*>(s_tab + p.off_wts);
+    const float* s_dct = reinterpret_cast<const float*>(s_tab + p.off_dct);
+    const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
+    const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
+    const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
+    float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes);
     float* s_logq = s_part + p.n_dst * geo::SLOTS;
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    int4* s_tasks = reinterpret_cast<int4*>(s_logq + n_lq * geo::SLOTS);
-    int32_t* s_tbeg = reinterpret_cast<int32_t*>(s_tasks + p.n_tasks);
-    int2* s_qspec = reinterpret_cast<int2*>(s_tbeg + ((geo::NGRP + 1 + 1) & ~1));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_logq + n_lq * geo::SLOTS);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-
-    // ---- one-time per CTA: tables into shared memory, exchange area zeroed (its never-written pad
-    //      words are later multiplied by zero weights and must not hold NaN bit patterns) -------------
-    for (int i = tid; i < kWarps * geo::XWARP / 4; i += kThreads)
-        reinterpret_cast<float4*>(s_xch)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < n_lq * geo::SLOTS; i += kThreads) s_logq[i] = 0.f;
-    for (int i = tid; i < 16 * 32; i += kThreads) s_tw4[i] = __ldg(p.tw4 + i);
-    for (int i = tid; i < p.n_wts4; i += kThreads) s_wts4[i] = __ldg(p.wts4 + i);
-    for (int i = tid; i < p.n_out * p.n_filt4; i += kThreads) s_dct[i] = __ldg(p.dct + i);
-    for (int i = tid; i < p.n_tasks; i += kThreads) s_tasks[i] = __ldg(reinterpret_cast<const int4*>(p.tasks) + i);
-    if (p.n_tasks > 0)
-        for (int i = tid; i <= geo::NGRP; i += kThreads) s_tbeg[i] = __ldg(p.task_begin + i);
-    for (int i = tid; i < p.n_q; i += kThreads) s_qspec[i] = __ldg(reinterpret_cast<const int2*>(p.qspec) + i);
-    __syncthreads();
-
     float* xw = s_xch + warp * geo::XWARP;
+
+    // ---- one-time per CTA -----------------------------------------------------------------------------------
+    // tables: ONE TMA bulk copy, waited for just before the first pass 2 (overlaps the first loads + pass 1)
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        bulk_g2s(s_tab, p.tables, (uint32_t)p.table_bytes, s_bar);
+    }
+    // the 16-byte pad of every exchange row is never written by pass 1 but aliases power-row words that the
+    // bank phase multiplies by zero weights: it must not hold NaN bit patterns
+#pragma unroll
+    for (int g = 0; g < geo::G; ++g)
+        *reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW + 2 * R) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n_lq * geo::SLOTS; i += kThreads) s_logq[i] = 0.f;
+
     // pass-2 role of this lane: pair g2 of the warp, column k1
     const int g2 = lane / R;
     const int k1 = lane % R;
@@ -157,39 +201,66 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
     }
 
     const InT* __restrict__ in = reinterpret_cast<const InT*>(p.in);
-    const int ppc = p.pairs_per_clip;
+    const uint32_t ppc = (uint32_t)p.pairs_per_clip;
+    const uint32_t n_pairs = (uint32_t)p.n_pairs;
+    bool tables_ready = false;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t pair0 = tile * geo::PPT;
+    // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
+    // of the current tile run (those need few registers), so the FFT stage never waits on HBM
+    InT raw[geo::G][geo::NLOAD];
+    auto prefetch = [&](uint32_t tile) {
+        if constexpr (FAST) {
+#pragma unroll
+            for (int g = 0; g < geo::G; ++g) {
+                const uint32_t gp = tile * geo::PPT + warp * geo::G + g;
+                if (gp < n_pairs) {
+                    const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
+                    const uint32_t q = gp - clip * ppc;
+                    const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
+                    const bool b_ok = (int)(2 * q + 1) < p.frames_per_clip;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) raw[g][j] = __ldg(src + 32 * j);
+#pragma unroll
+                    for (int j = R; j < geo::NLOAD; ++j) raw[g][j] = b_ok ? __ldg(src + 32 * j) : (InT)0;
+                }
+            }
+        }
+    };
+    if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
+    __syncthreads();          // mbarrier init + pads visible
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t pair0 = tile * geo::PPT;
 
         // =========================== FFT stage (per warp) =======================================
-        if (pair0 + warp * geo::G < p.n_pairs) {
+        if (pair0 + warp * geo::G < n_pairs) {
             // ---- pass 1: lane = n2; R-point FFT over n1 of z[n2 + 32 n1], z = A + iB ----------------
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
-                const int64_t gp = pair0 + warp * geo::G + g;
-                if (gp < p.n_pairs) {
-                    const int64_t clip = gp / ppc;
-                    const int q = (int)(gp - clip * ppc);
-                    const InT* __restrict__ cb = in + clip * p.clip_stride;
+                const uint32_t gp = pair0 + warp * geo::G + g;
+                if (gp < n_pairs) {
                     float xr[R], xi[R];
                     if constexpr (FAST) {
-                        // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half
-                        // their samples; lane reads x[1024q + lane + 32 j], j < R + R/2.
-                        const InT* __restrict__ src = cb + (int64_t)q * geo::NFFT + lane;
-                        const bool b_ok = (2 * q + 1) < p.frames_per_clip;
-                        float s[geo::NLOAD];
-#pragma unroll
-                        for (int j = 0; j < R; ++j) s[j] = to_f32(__ldg(src + 32 * j));
-#pragma unroll
-                        for (int j = R; j < geo::NLOAD; ++j) s[j] = b_ok ? to_f32(__ldg(src + 32 * j)) : 0.f;
+                        // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half their
+                        // samples; raw[g][j] = x[n_fft*q + lane + 32 j], j < R + R/2 (zeros where frame B is absent)
 #pragma unroll
                         for (int i = 0; i < R; ++i) {
                             const int n1 = scf_bitrev(i, geo::LOG2R);
-                            xr[i] = s[n1];
-                            xi[i] = b_ok ? s[n1 + R / 2] : 0.f;
+                            xr[i] = to_f32(raw[g][n1]);
+                            xi[i] = to_f32(raw[g][n1 + R / 2]);
+                        }
+                        if (p.frames_per_clip & 1) {
+                            const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
+                            const uint32_t q = gp - clip * ppc;
+                            if ((int)(2 * q + 1) >= p.frames_per_clip) {          // frame B absent (odd frame count)
+#pragma unroll
+                                for (int i = 0; i < R; ++i) xi[i] = 0.f;
+                            }
                         }
                     } else {
+                        const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
+                        const int q = (int)(gp - clip * ppc);
+                        const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
                         load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
                         load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
@@ -201,6 +272,10 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
                 }
             }
             __syncwarp();
+            if (!tables_ready) {          // first tile only: the twiddles arrive with the table blob
+                mbar_wait(s_bar, 0);
+                tables_ready = true;
+            }
 
             // ---- pass 2: lane = (pair g2, column k1); twiddle, 32-point FFT over n2 -> Z[k1 + R k2] --
             float yr[32], yi[32];
@@ -225,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
             float2* mir = reinterpret_cast<float2*>(xw + g2 * geo::MIR);
 #pragma unroll
             for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = make_float2(yr[k2], yi[k2]);
-            if (k1 == 0) mir[geo::NB] = make_float2(yr[0], yi[0]);       // Z[N] == Z[0]
+            mir[k1 == 0 ? geo::NB : geo::NB + 1] = make_float2(yr[0], yi[0]);      // Z[N] == Z[0]; NB+1 is a dump slot
             __syncwarp();
             float* pa_row = pw + (2 * g2) * geo::PROW;
             float* pb_row = pa_row + geo::PROW;
@@ -242,34 +317,38 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
                 pa_row[geo::NB] = 4.f * yr[16] * yr[16];
                 pb_row[geo::NB] = 4.f * yi[16] * yi[16];
             }
+        } else if (!tables_ready) {
+            mbar_wait(s_bar, 0);
+            tables_ready = true;
         }
+        if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
         __syncthreads();
 
         // =========================== where this thread's slot goes ==============================
         int64_t out_row = -1;
         {
-            const int64_t gp = pair0 + (slot >> 1);
-            if (gp < p.n_pairs) {
-                const int64_t clip = gp / ppc;
+            const uint32_t gp = pair0 + (slot >> 1);
+            if (gp < n_pairs) {
+                const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
                 const int f = 2 * (int)(gp - clip * ppc) + (slot & 1);
                 int nfr = p.frames_per_clip;
                 if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
-                if (f < nfr) out_row = clip * p.frames_per_clip + f;
+                if (f < nfr) out_row = (int64_t)clip * p.frames_per_clip + f;
             }
         }
 
         if (p.out_kind == SCF_OUT_POWER) {
-            // power_spec(): rows straight out of shared memory, coalesced along the bins
+            // power_spec(): rows straight out of shared memory, coalesced along the bins;
             // warp w copies slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
             for (int s = warp; s < geo::SLOTS; s += kWarps) {
-                const int64_t gp = pair0 + (s >> 1);
+                const uint32_t gp = pair0 + (s >> 1);
                 int64_t row = -1;
-                if (gp < p.n_pairs) {
-                    const int64_t clip = gp / ppc;
+                if (gp < n_pairs) {
+                    const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
                     const int f = 2 * (int)(gp - clip * ppc) + (s & 1);
                     int nfr = p.frames_per_clip;
                     if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
-                    if (f < nfr) row = clip * p.frames_per_clip + f;
+                    if (f < nfr) row = (int64_t)clip * p.frames_per_clip + f;
                 }
                 if (row < 0) continue;
                 const int sw = s / (2 * geo::G), ls = s % (2 * geo::G);
@@ -282,15 +361,17 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
         }
 
         // =========================== bank stage ================================================
+        // tasks are runs of exactly 16 bins (4 float4) of one filter; consecutive tasks of a run accumulate in
+        // a register and the task flagged `last` stores the run's partial sum
         {
             const int t_end = s_tbeg[grp + 1];
+            float acc0 = 0.f, acc1 = 0.f;
             for (int t = s_tbeg[grp]; t < t_end; ++t) {
-                const int4 tk = s_tasks[t];
-                const float4* pp = reinterpret_cast<const float4*>(prow_slot + tk.x);
-                const float4* ww = s_wts4 + tk.z;
-                float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 2
-                for (int i = 0; i < tk.y; ++i) {
+                const uint32_t tk = s_tasks[t];
+                const float4* pp = reinterpret_cast<const float4*>(prow_slot + (tk & 0xfffu));
+                const float4* ww = s_wts4 + 4 * t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
                     const float4 a = pp[i];
                     const float4 w = ww[i];
                     acc0 = __fmaf_rn(a.x, w.x, acc0);
@@ -298,7 +379,11 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
                     acc0 = __fmaf_rn(a.z, w.z, acc0);
                     acc1 = __fmaf_rn(a.w, w.w, acc1);
                 }
-                s_part[tk.w * geo::SLOTS + slot] = acc0 + acc1;
+                if (tk & 0x80000000u) {
+                    s_part[((tk >> 12) & 0xfffu) * geo::SLOTS + slot] = acc0 + acc1;
+                    acc0 = 0.f;
+                    acc1 = 0.f;
+                }
             }
         }
         __syncthreads();
@@ -306,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
         // =========================== log ========================================================
         for (int q = grp; q < p.n_q; q += geo::NGRP) {
             const int2 qs = s_qspec[q];
-            float v = 0.f;
-            for (int j = 0; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
+            float v = s_part[qs.x * geo::SLOTS + slot];
+            for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
             const float lv = logf(fmaxf(v, SCF_EPS));
             if (p.out_kind == SCF_OUT_LOG_BANK) {
                 if (out_row >= 0) {
@@ -325,28 +410,37 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
         __syncthreads();
 
         // =========================== DCT-II, c0 := log energy ===================================
-        for (int c = grp; c < p.n_out; c += geo::NGRP) {
-            float v;
-            if (c == 0) {
-                v = s_logq[p.n_filt * geo::SLOTS + slot];
-            } else {
-                const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
-                float a0 = 0.f, a1 = 0.f;
-                for (int m = 0; m < p.n_filt4; m += 4) {
-                    const float4 d = d4[m >> 2];
-                    // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
-                    a0 = __fmaf_rn(s_logq[(m + 0) * geo::SLOTS + slot], d.x, a0);
-                    a1 = __fmaf_rn(s_logq[(m + 1) * geo::SLOTS + slot], d.y, a1);
-                    a0 = __fmaf_rn(s_logq[(m + 2) * geo::SLOTS + slot], d.z, a0);
-                    a1 = __fmaf_rn(s_logq[(m + 3) * geo::SLOTS + slot], d.w, a1);
-                }
-                v = a0 + a1;
+        // each thread produces two coefficients of its slot so that the log-band loads are shared
+        for (int c = 2 * grp; c < p.n_out; c += 2 * geo::NGRP) {
+            const bool two = (c + 1) < p.n_out;
+            const float4* d4a = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
+            const float4* d4b = reinterpret_cast<const float4*>(s_dct + (two ? c + 1 : c) * p.n_filt4);
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            for (int m = 0; m < p.n_filt4; m += 4) {
+                // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
+                const float l0 = s_logq[(m + 0) * geo::SLOTS + slot], l1 = s_logq[(m + 1) * geo::SLOTS + slot];
+                const float l2 = s_logq[(m + 2) * geo::SLOTS + slot], l3 = s_logq[(m + 3) * geo::SLOTS + slot];
+                const float4 da = d4a[m >> 2];
+                const float4 db = d4b[m >> 2];
+                a0 = __fmaf_rn(l0, da.x, a0); a1 = __fmaf_rn(l1, da.y, a1);
+                a0 = __fmaf_rn(l2, da.z, a0); a1 = __fmaf_rn(l3, da.w, a1);
+                b0 = __fmaf_rn(l0, db.x, b0); b1 = __fmaf_rn(l1, db.y, b1);
+                b0 = __fmaf_rn(l2, db.z, b0); b1 = __fmaf_rn(l3, db.w, b1);
             }
+            float va = a0 + a1;
+            const float vb = b0 + b1;
+            if (c == 0) va = s_logq[p.n_filt * geo::SLOTS + slot];
             if (out_row >= 0) {
                 if (p.n_peers == 0) {
-                    p.out[out_row * p.out_cols + c] = v;
+                    float* o = p.out + out_row * p.out_cols + c;
+                    o[0] = va;
+                    if (two) o[1] = vb;
                 } else {
-                    for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(p.peer_row0 + out_row) * p.out_cols + c] = v;
+                    for (int r = 0; r < p.n_peers; ++r) {
+                        float* o = p.peer_out[r] + (p.peer_row0 + out_row) * p.out_cols + c;
+                        o[0] = va;
+                        if (two) o[1] = vb;
+                    }
                 }
             }
         }
@@ -360,9 +454,8 @@ template <int R>
 static size_t smem_bytes_r(const KParams& p)
 {
     using geo = Geo<R>;
-    size_t f = (size_t)kWarps * geo::XWARP + 16 * 32 * 4 + (size_t)p.n_wts4 * 4 + (size_t)p.n_out * p.n_filt4 +
-               (size_t)p.n_dst * geo::SLOTS + (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4) * geo::SLOTS;
-    size_t b = f * 4 + (size_t)p.n_tasks * 16 + (size_t)((geo::NGRP + 2) & ~1) * 4 + (size_t)p.n_q * 8;
+    const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
+    size_t b = (size_t)kWarps * geo::XWARP * 4 + (size_t)p.table_bytes + ((size_t)p.n_dst + n_lq) * geo::SLOTS * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -378,12 +471,18 @@ template <int R, typename InT, bool FAST>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
 {
     auto kern = extract_kernel<R, InT, FAST>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static size_t configured[16] = {0};          // per device: the attribute call costs microseconds per launch
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 15] = smem;
+    }
     int64_t grid = (int64_t)num_sms * 2;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, n_tiles);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, (uint32_t)n_tiles);
     count_launch(1);
     return cudaGetLastError();
 }
