@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
     const int warp = tid >> 5;
     float* xw = s_xch + warp * geo::XWARP;
 
+    // Programmatic dependent launch: let the NEXT extract launch of the stream start filling SMs as soon as
+    // this grid's CTAs retire (its loads / FFTs do not depend on us).  Every extract grid waits for its
+    // predecessor (griddepcontrol.wait below) before its first global store, so output ordering is kept;
+    // kernels launched without the attribute (everything else in the stream) still wait for full completion.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool deps_done = false;
+
     // ---- one-time per CTA -----------------------------------------------------------------------------------
     // tables: ONE TMA bulk copy, waited for just before the first pass 2 (overlaps the first loads + pass 1)
     if (tid == 0) {
@@ -322,6 +329,10 @@ __global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, c
             tables_ready = true;
         }
         if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+        if (!deps_done) {         // before this grid's first global store
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            deps_done = true;
+        }
         __syncthreads();
 
         // =========================== where this thread's slot goes ==============================
@@ -482,7 +493,18 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
     int64_t grid = (int64_t)num_sms * 2;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(p, (uint32_t)n_tiles);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p, (uint32_t)n_tiles);
+    if (le != cudaSuccess) return le;
     count_launch(1);
     return cudaGetLastError();
 }
