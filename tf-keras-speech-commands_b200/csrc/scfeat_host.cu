@@ -165,6 +165,8 @@ struct Workspace {          // scratch for the host-buffer entry points
     int32_t* d_len = nullptr;
     size_t len_bytes = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev = nullptr;
 };
 
 }  // namespace scf
@@ -337,6 +339,8 @@ static void free_plan_tables(scf_plan* p)
     if (p->ws.d_out) cudaFree(p->ws.d_out);
     if (p->ws.d_len) cudaFree(p->ws.d_len);
     if (p->ws.st) cudaStreamDestroy(p->ws.st);
+    if (p->ws.st2) cudaStreamDestroy(p->ws.st2);
+    if (p->ws.ev) cudaEventDestroy(p->ws.ev);
 }
 
 static int plan_create(const scf_config* cfg, scf_plan** out)
@@ -523,7 +527,7 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
     DeviceGuard guard(plan->device);
     if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
     const size_t smem = extract_smem_bytes(plan->radix_r, kp);
-    if (smem > 113 * 1024) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
+    if (smem > (size_t)(227 * 1024) / kCtasPerSm - 1024) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
     // the kernel indexes pairs with 32 bits: very large jobs go out as several launches
     const int ppt = pairs_per_tile(plan->radix_r);
     const int64_t max_clips = std::max<int64_t>(1, (0x7fffffffLL - ppt) / std::max(1, kp.pairs_per_clip));
@@ -570,9 +574,12 @@ static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int
     Workspace& ws = const_cast<scf_plan*>(plan)->ws;
     std::lock_guard<std::mutex> lock(ws.mu);
     if (!ws.st) SCF_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+    if (!ws.st2) SCF_CUDA(cudaStreamCreateWithFlags(&ws.st2, cudaStreamNonBlocking));
+    if (!ws.ev) SCF_CUDA(cudaEventCreateWithFlags(&ws.ev, cudaEventDisableTiming));
     const size_t esz = is_f32 ? 4 : 2;
     const size_t in_bytes = (size_t)((n_clips - 1) * clip_stride + clip_len) * esz;
-    const size_t out_bytes = (size_t)n_clips * fpc * plan->out_cols * sizeof(float);
+    const size_t row_bytes = (size_t)fpc * plan->out_cols * sizeof(float);
+    const size_t out_bytes = (size_t)n_clips * row_bytes;
     int rc;
     if ((rc = grow(&ws.d_in, &ws.in_bytes, in_bytes)) || (rc = grow(&ws.d_out, &ws.out_bytes, out_bytes))) return rc;
     const int32_t* d_len = nullptr;
@@ -581,13 +588,33 @@ static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int
         SCF_CUDA(cudaMemcpyAsync(ws.d_len, h_lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, ws.st));
         d_len = ws.d_len;
     }
-    SCF_CUDA(cudaMemcpyAsync(ws.d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ws.st));
     if (pad == SCF_PAD_NONE && h_lengths)      // rows of short clips stay untouched by the kernel: make them zero
         SCF_CUDA(cudaMemsetAsync(ws.d_out, 0, out_bytes, ws.st));
-    rc = extract_device(plan, is_f32, ws.d_in, n_clips, clip_stride, clip_len, d_len, pad, ws.d_out, nullptr, 0, 0, ws.st);
-    if (rc) return rc;
-    SCF_CUDA(cudaMemcpyAsync(h_out, ws.d_out, out_bytes, cudaMemcpyDeviceToHost, ws.st));
+    SCF_CUDA(cudaEventRecord(ws.ev, ws.st));
+    SCF_CUDA(cudaStreamWaitEvent(ws.st2, ws.ev, 0));
+    // Chunks of >= 2 MB of input alternate between two streams so that the H2D copy of chunk i+1 overlaps the
+    // kernel and the D2H copy of chunk i (separate copy engines); every chunk owns a disjoint slice of the
+    // staging buffers, so there is nothing to recycle.
+    const size_t clip_bytes = (size_t)clip_stride * esz;
+    int64_t chunk = std::max<int64_t>(1, (int64_t)((2u << 20) / std::max<size_t>(clip_bytes, 1)));
+    if (n_clips < 2 * chunk) chunk = n_clips;
+    int which = 0;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += chunk, which ^= 1) {
+        const int64_t nc = std::min(chunk, n_clips - c0);
+        cudaStream_t st = which ? ws.st2 : ws.st;
+        const unsigned char* h_src = static_cast<const unsigned char*>(h_in) + (size_t)c0 * clip_bytes;
+        unsigned char* d_src = static_cast<unsigned char*>(ws.d_in) + (size_t)c0 * clip_bytes;
+        const size_t bytes = (size_t)((nc - 1) * clip_stride + clip_len) * esz;
+        SCF_CUDA(cudaMemcpyAsync(d_src, h_src, bytes, cudaMemcpyHostToDevice, st));
+        float* d_dst = ws.d_out + (size_t)c0 * fpc * plan->out_cols;
+        rc = extract_device(plan, is_f32, d_src, nc, clip_stride, clip_len, d_len ? d_len + c0 : nullptr, pad, d_dst,
+                            nullptr, 0, 0, st);
+        if (rc) { cudaStreamSynchronize(ws.st); cudaStreamSynchronize(ws.st2); return rc; }
+        SCF_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(h_out) + (size_t)c0 * row_bytes, d_dst,
+                                 (size_t)nc * row_bytes, cudaMemcpyDeviceToHost, st));
+    }
     SCF_CUDA(cudaStreamSynchronize(ws.st));
+    SCF_CUDA(cudaStreamSynchronize(ws.st2));
     return SCF_OK;
 }
 

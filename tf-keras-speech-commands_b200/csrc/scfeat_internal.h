@@ -11,6 +11,7 @@ namespace scf {
 
 constexpr int kWarps = 8;                 // warps per CTA
 constexpr int kThreads = kWarps * 32;
+constexpr int kCtasPerSm = 16 / kWarps;    // 16 warps per SM at <= 128 registers per thread
 constexpr int kMaxPeers = 8;
 
 // Bank-phase task word: a run of exactly 16 consecutive bins (4 float4) of one filter.

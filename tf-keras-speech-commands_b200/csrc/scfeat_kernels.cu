@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
 }
 
 template <int R, typename InT, bool FAST>
-__global__ void __launch_bounds__(kThreads, 2) extract_kernel(const KParams p, const uint32_t n_tiles)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KParams p, const uint32_t n_tiles)
 {
     using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
@@ -490,7 +490,7 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
         if (e != cudaSuccess) return e;
         configured[dev & 15] = smem;
     }
-    int64_t grid = (int64_t)num_sms * 2;
+    int64_t grid = (int64_t)num_sms * kCtasPerSm;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};

@@ -43,8 +43,9 @@ class Plan:
         return _lib.num_frames(n_samples, self.window, self.hop)
 
     # ---- host numpy in -> host numpy out (what the drop-in functions use) ----------------------
-    def extract_host(self, clips, lengths=None, pad=PAD_FRONT_ZERO):
-        """clips: [n, L] (or [L]) int16 PCM or float32 audio.  Returns float32 [n, frames(L), cols]."""
+    def extract_host(self, clips, lengths=None, pad=PAD_FRONT_ZERO, out=None):
+        """clips: [n, L] (or [L]) int16 PCM or float32 audio.  Returns float32 [n, frames(L), cols].
+        `out` may be a preallocated C-contiguous float32 array of that shape (e.g. pinned memory) to write into."""
         a = np.asarray(clips)
         single = a.ndim == 1
         if single:
@@ -58,7 +59,11 @@ class Plan:
             fn = _lib.lib().scf_extract_host_f32
         a = np.ascontiguousarray(a)
         n, L = a.shape
-        out = np.zeros((n, self.frames(L), self.out_cols), dtype=np.float32)
+        shape = (n, self.frames(L), self.out_cols)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        elif out.shape != shape or out.dtype != np.float32 or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a C-contiguous float32 array of shape %r' % (shape,))
         lp = None
         if lengths is not None:
             lengths = np.ascontiguousarray(lengths, dtype=np.int32)
