@@ -181,6 +181,18 @@ int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n
 int scf_allgather_nccl(void* nccl_comm, const float* d_local, int64_t n_local_floats, float* d_all,
                        void* cuda_stream);
 
+/* Device-memory and CUDA-IPC helpers so that a ctypes host can own a peer-mappable feature cache without
+ * any other CUDA binding: scf_device_malloc returns plain cudaMalloc memory (exportable); scf_ipc_export /
+ * scf_ipc_import wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle (64-byte handle, peer access enabled lazily).
+ * scf_memcpy: kind 0 = host->device, 1 = device->host, 2 = device->device; synchronous when cuda_stream is
+ * NULL. */
+int scf_device_malloc(int32_t device, int64_t bytes, void** d_ptr_out);
+int scf_device_free(int32_t device, void* d_ptr);
+int scf_memcpy(int32_t device, void* dst, const void* src, int64_t bytes, int32_t kind, void* cuda_stream);
+int scf_ipc_export(int32_t device, void* d_ptr, uint8_t* handle64_out);
+int scf_ipc_import(int32_t device, const uint8_t* handle64, void** d_ptr_out);
+int scf_ipc_close(int32_t device, void* d_ptr);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* scf_last_error(void);
 int scf_version(void);

@@ -29,7 +29,8 @@ EXPORTS = [
     'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_allgather_nccl',
     'scf_stream_create', 'scf_stream_destroy', 'scf_stream_reset', 'scf_stream_push_i16',
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
-    'scf_measure_fp32_flops',
+    'scf_measure_fp32_flops', 'scf_device_malloc', 'scf_device_free', 'scf_memcpy', 'scf_ipc_export',
+    'scf_ipc_import', 'scf_ipc_close',
 ]
 
 
@@ -109,6 +110,12 @@ def lib():
         L.scf_version.restype = i32
         L.scf_launch_count.restype = i64
         L.scf_measure_fp32_flops.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
+        L.scf_device_malloc.argtypes = [i32, i64, ctypes.POINTER(vp)]
+        L.scf_device_free.argtypes = [i32, vp]
+        L.scf_memcpy.argtypes = [i32, vp, vp, i64, i32, vp]
+        L.scf_ipc_export.argtypes = [i32, vp, vp]
+        L.scf_ipc_import.argtypes = [i32, vp, ctypes.POINTER(vp)]
+        L.scf_ipc_close.argtypes = [i32, vp]
         _lib = L
         return _lib
 

@@ -821,6 +821,73 @@ int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n
                           d_peer_out, world, rank, cuda_stream);
 }
 
+// ---- device memory / CUDA IPC helpers ------------------------------------------------------------
+int scf_device_malloc(int32_t device, int64_t bytes, void** d_ptr_out)
+{
+    if (!d_ptr_out || bytes < 0) return fail(SCF_ERR_INVALID, "bad argument");
+    *d_ptr_out = nullptr;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    SCF_CUDA(cudaMalloc(d_ptr_out, (size_t)std::max<int64_t>(bytes, 256)));
+    return SCF_OK;
+}
+
+int scf_device_free(int32_t device, void* d_ptr)
+{
+    if (!d_ptr) return SCF_OK;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    SCF_CUDA(cudaFree(d_ptr));
+    return SCF_OK;
+}
+
+int scf_memcpy(int32_t device, void* dst, const void* src, int64_t bytes, int32_t kind, void* cuda_stream)
+{
+    if (bytes < 0 || kind < 0 || kind > 2) return fail(SCF_ERR_INVALID, "bad argument");
+    if (bytes == 0) return SCF_OK;
+    if (!dst || !src) return fail(SCF_ERR_INVALID, "NULL pointer");
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    SCF_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)cuda_stream));
+    if (!cuda_stream) SCF_CUDA(cudaStreamSynchronize(nullptr));
+    return SCF_OK;
+}
+
+int scf_ipc_export(int32_t device, void* d_ptr, uint8_t* handle64_out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!d_ptr || !handle64_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    SCF_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64_out, &h, 64);
+    return SCF_OK;
+}
+
+int scf_ipc_import(int32_t device, const uint8_t* handle64, void** d_ptr_out)
+{
+    if (!handle64 || !d_ptr_out) return fail(SCF_ERR_INVALID, "NULL argument");
+    *d_ptr_out = nullptr;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SCF_CUDA(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SCF_OK;
+}
+
+int scf_ipc_close(int32_t device, void* d_ptr)
+{
+    if (!d_ptr) return SCF_OK;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    SCF_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return SCF_OK;
+}
+
 // ---- NCCL (resolved lazily; the library itself does not link against libnccl) -------------------
 int scf_allgather_nccl(void* nccl_comm, const float* d_local, int64_t n_local_floats, float* d_all, void* cuda_stream)
 {
