@@ -168,13 +168,14 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
 
 /* ---- multi-GPU feature-cache assembly (new; the reference is single-process) ------------------ */
 
-/* Fused extract + all-gather over NVLink peer memory: this rank extracts its n_local clips and the
- * kernel epilogue stores every row into the same slot of all `world` ranks' caches
- * (d_peer_out[r] = base of rank r's full [world*n_local, frames, cols] cache, peer-mapped).
+/* Fused extract + all-gather over NVLink peer memory: this rank extracts its n_local clips and the kernel
+ * epilogue stores every row into the same slot of all `world` ranks' caches
+ * (d_peer_out[r] = base of rank r's full [world*clips_per_rank, frames, cols] cache, peer-mapped; this rank's
+ * block starts at row rank*clips_per_rank*frames; n_local <= clips_per_rank, the last rank may own fewer).
  * The caller owns the cross-rank barrier that follows. */
 int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
                            int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank,
-                           void* cuda_stream);
+                           int64_t clips_per_rank, void* cuda_stream);
 
 /* Plain NCCL all-gather of per-rank feature shards (baseline for the fused path).  nccl_comm is an
  * ncclComm_t; libnccl.so.2 is resolved with dlopen at first use. */

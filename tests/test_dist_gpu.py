@@ -41,7 +41,7 @@ def test_emulated_ranks_fill_every_cache(example_pcm, n_clips, world):
         start, count, _ = shard_range(n_clips, world, r)
         if count:
             _lib.check(L.scf_extract_i16_gather(plan.handle, d_pcm[start].data_ptr(), count, 16000, 16000, table, world, r,
-                                                st.cuda_stream))
+                                                per, st.cuda_stream))
     st.synchronize()
     want = plan.extract_host(pcm)
     ref = np.stack([osonopy.mfcc_spec(c.astype(np.float32) / 32768.0, 16000, (1024, 512), 1024, 20, 20) for c in pcm[:8]])

@@ -98,7 +98,7 @@ def lib():
         L.scf_extract_host_i16.argtypes = host_args
         L.scf_extract_host_f32.argtypes = host_args
         L.scf_extract_i16_dlpack.argtypes = [vp, vp, i64, i64, i32, vp, i32, ctypes.POINTER(vp), vp]
-        L.scf_extract_i16_gather.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(vp), i32, i32, vp]
+        L.scf_extract_i16_gather.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(vp), i32, i32, i64, vp]
         L.scf_allgather_nccl.argtypes = [vp, vp, i64, vp, vp]
         L.scf_stream_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(vp)]
         L.scf_stream_destroy.argtypes = [vp]

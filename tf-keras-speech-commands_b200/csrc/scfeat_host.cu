@@ -502,7 +502,7 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
 
 static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out,
-                          float* const* peers, int world, int rank, void* cuda_stream)
+                          float* const* peers, int world, int rank, void* cuda_stream, int64_t clips_per_rank = 0)
 {
     if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
     KParams kp;
@@ -519,7 +519,8 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
             if (!peers[r]) return fail(SCF_ERR_INVALID, "peer pointer is NULL");
             kp.peer_out[r] = peers[r];
         }
-        kp.peer_row0 = (int64_t)rank * n_clips * kp.frames_per_clip;
+        if (clips_per_rank < n_clips) return fail(SCF_ERR_INVALID, "clips_per_rank must be >= n_local");
+        kp.peer_row0 = (int64_t)rank * clips_per_rank * kp.frames_per_clip;
     } else if (n_clips > 0 && kp.frames_per_clip > 0 && !d_out) {
         return fail(SCF_ERR_INVALID, "output pointer is NULL");
     }
@@ -814,11 +815,12 @@ void* scf_dlpack_make_capsule(void* dl_managed_tensor)
 }
 
 int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
-                           int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank, void* cuda_stream)
+                           int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank,
+                           int64_t clips_per_rank, void* cuda_stream)
 {
     if (!d_peer_out) return fail(SCF_ERR_INVALID, "peer table is NULL");
     return extract_device(plan, false, d_pcm, n_local, clip_stride, clip_len, nullptr, SCF_PAD_FRONT_ZERO, nullptr,
-                          d_peer_out, world, rank, cuda_stream);
+                          d_peer_out, world, rank, cuda_stream, clips_per_rank);
 }
 
 // ---- device memory / CUDA IPC helpers ------------------------------------------------------------

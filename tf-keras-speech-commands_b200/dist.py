@@ -79,7 +79,7 @@ class FeatureCacheGather:
             return
         check(_lib.lib().scf_extract_i16_gather(self.plan.handle, d_pcm_local, self.count,
                                                 self.clip_len if clip_stride is None else clip_stride,
-                                                self.clip_len, self._table, self.world, self.rank, stream))
+                                                self.clip_len, self._table, self.world, self.rank, self.per_rank, stream))
 
     def to_host(self):
         """The first n_clips rows of this rank's cache as float32 numpy [n_clips, frames, cols]
