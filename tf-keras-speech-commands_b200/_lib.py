@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libscfeat.so')
+# SCFEAT_LIB lets the kernel-tuning scripts load an experimental build; the product default is the in-tree library
+LIB_PATH = os.environ.get('SCFEAT_LIB') or os.path.join(_HERE, 'libscfeat.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 # enums of include/scfeat.h

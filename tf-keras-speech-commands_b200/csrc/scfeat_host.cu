@@ -313,6 +313,11 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
                 tl.words.push_back(word);
                 tl.weights.insert(tl.weights.end(), w_of[r][t].begin(), w_of[r][t].end());
             }
+        // the kernel consumes two tasks per iteration (8-byte aligned pairs): pad with a null task
+        if ((tl.words.size() - (size_t)tl.begin[g]) & 1) {
+            tl.words.push_back(0u);
+            tl.weights.insert(tl.weights.end(), kTaskBins, 0.0);
+        }
     }
     tl.begin[n_groups] = (int32_t)tl.words.size();
 }

@@ -25,6 +25,13 @@
 
 namespace scf {
 
+#ifndef SCF_PREFETCH_IN_MIRROR
+#define SCF_PREFETCH_IN_MIRROR 1
+#endif
+#ifndef SCF_BANK_PAIRS
+#define SCF_BANK_PAIRS 1
+#endif
+
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
 
 template <int R>
@@ -309,6 +316,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
             for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = make_float2(yr[k2], yi[k2]);
             mir[k1 == 0 ? geo::NB : geo::NB + 1] = make_float2(yr[0], yi[0]);      // Z[N] == Z[0]; NB+1 is a dump slot
             __syncwarp();
+#if SCF_PREFETCH_IN_MIRROR
+            // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
+            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+#endif
             float* pa_row = pw + (2 * g2) * geo::PROW;
             float* pb_row = pa_row + geo::PROW;
 #pragma unroll
@@ -324,11 +335,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                 pa_row[geo::NB] = 4.f * yr[16] * yr[16];
                 pb_row[geo::NB] = 4.f * yi[16] * yi[16];
             }
-        } else if (!tables_ready) {
-            mbar_wait(s_bar, 0);
-            tables_ready = true;
+#if !SCF_PREFETCH_IN_MIRROR
+            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+#endif
+        } else {
+            if (!tables_ready) {
+                mbar_wait(s_bar, 0);
+                tables_ready = true;
+            }
+            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
         }
-        if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
         if (!deps_done) {         // before this grid's first global store
             asm volatile("griddepcontrol.wait;" ::: "memory");
             deps_done = true;
@@ -373,10 +389,55 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
 
         // =========================== bank stage ================================================
         // tasks are runs of exactly 16 bins (4 float4) of one filter; consecutive tasks of a run accumulate in
-        // a register and the task flagged `last` stores the run's partial sum
+        // registers and the task flagged `last` stores the run's partial sum.  Every group's list is padded to an
+        // even length (null tasks: zero weights), two tasks are in flight per iteration and the next pair of task
+        // words is fetched one iteration ahead, so the shared-memory round trips overlap the FMAs.
+#if SCF_BANK_PAIRS
         {
             const int t_end = s_tbeg[grp + 1];
-            float acc0 = 0.f, acc1 = 0.f;
+            int t = s_tbeg[grp];
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+            uint2 tk = make_uint2(0u, 0u);
+            if (t < t_end) tk = *reinterpret_cast<const uint2*>(s_tasks + t);
+            for (; t < t_end; t += 2) {
+                const float4* pa4 = reinterpret_cast<const float4*>(prow_slot + (tk.x & 0xfffu));
+                const float4* pb4 = reinterpret_cast<const float4*>(prow_slot + (tk.y & 0xfffu));
+                const float4* ww = s_wts4 + 4 * t;
+                float4 a[4], b[4], wa[4], wb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = pa4[i]; wa[i] = ww[i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { b[i] = pb4[i]; wb[i] = ww[4 + i]; }
+                const uint2 cur = tk;
+                if (t + 2 < t_end) tk = *reinterpret_cast<const uint2*>(s_tasks + t + 2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc0 = __fmaf_rn(a[i].x, wa[i].x, acc0);
+                    acc1 = __fmaf_rn(a[i].y, wa[i].y, acc1);
+                    acc2 = __fmaf_rn(a[i].z, wa[i].z, acc2);
+                    acc3 = __fmaf_rn(a[i].w, wa[i].w, acc3);
+                }
+                if (cur.x & 0x80000000u) {
+                    s_part[((cur.x >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
+                    acc0 = acc1 = acc2 = acc3 = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc0 = __fmaf_rn(b[i].x, wb[i].x, acc0);
+                    acc1 = __fmaf_rn(b[i].y, wb[i].y, acc1);
+                    acc2 = __fmaf_rn(b[i].z, wb[i].z, acc2);
+                    acc3 = __fmaf_rn(b[i].w, wb[i].w, acc3);
+                }
+                if (cur.y & 0x80000000u) {
+                    s_part[((cur.y >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
+                    acc0 = acc1 = acc2 = acc3 = 0.f;
+                }
+            }
+        }
+#else
+        {
+            const int t_end = s_tbeg[grp + 1];
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
             for (int t = s_tbeg[grp]; t < t_end; ++t) {
                 const uint32_t tk = s_tasks[t];
                 const float4* pp = reinterpret_cast<const float4*>(prow_slot + (tk & 0xfffu));
@@ -387,16 +448,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                     const float4 w = ww[i];
                     acc0 = __fmaf_rn(a.x, w.x, acc0);
                     acc1 = __fmaf_rn(a.y, w.y, acc1);
-                    acc0 = __fmaf_rn(a.z, w.z, acc0);
-                    acc1 = __fmaf_rn(a.w, w.w, acc1);
+                    acc2 = __fmaf_rn(a.z, w.z, acc2);
+                    acc3 = __fmaf_rn(a.w, w.w, acc3);
                 }
                 if (tk & 0x80000000u) {
-                    s_part[((tk >> 12) & 0xfffu) * geo::SLOTS + slot] = acc0 + acc1;
-                    acc0 = 0.f;
-                    acc1 = 0.f;
+                    s_part[((tk >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
+                    acc0 = acc1 = acc2 = acc3 = 0.f;
                 }
             }
         }
+#endif
         __syncthreads();
 
         // =========================== log ========================================================
@@ -404,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
             const int2 qs = s_qspec[q];
             float v = s_part[qs.x * geo::SLOTS + slot];
             for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
-            const float lv = logf(fmaxf(v, SCF_EPS));
+            const float lv = __logf(fmaxf(v, SCF_EPS));          // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
             if (p.out_kind == SCF_OUT_LOG_BANK) {
                 if (out_row >= 0) {
                     if (p.n_peers == 0) {

@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""A/B timing of libscfeat builds: for every library given (or the product build), times the bench workload
+(512-clip batches back to back, 16-batch pool) and a large batch.  Each library runs in its own process.
+Usage: python tools/ab.py [lib.so ...]"""
+import os
+import subprocess
+import sys
+
+CHILD = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+import scfeat
+plan = scfeat.get_plan()
+st = torch.cuda.current_stream()
+g = torch.Generator(device='cuda'); g.manual_seed(0)
+pool = torch.randint(-32768, 32768, (16, 512, 16000), dtype=torch.int16, device='cuda', generator=g)
+out = torch.empty((512, 30, 20), dtype=torch.float32, device='cuda')
+def run(k):
+    for i in range(k):
+        plan.extract_device(pool[i % 16].data_ptr(), 512, 16000, out.data_ptr(), stream=st.cuda_stream)
+run(50); torch.cuda.synchronize()
+best = 1e9
+for rep in range(5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(1000); e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 1000)
+big = pool.view(8192, 16000)
+bout = torch.empty((8192, 30, 20), dtype=torch.float32, device='cuda')
+bb = 1e9
+for rep in range(8):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); plan.extract_device(big.data_ptr(), 8192, 16000, bout.data_ptr(), stream=st.cuda_stream); e1.record(); torch.cuda.synchronize()
+    bb = min(bb, e0.elapsed_time(e1))
+print('%-28s  512-batch %.2f us/step = %.2f M clips/s | 8192 clips %.1f us = %.2f M clips/s' % (
+    os.path.basename(os.environ.get('SCFEAT_LIB', 'product')), best * 1e3, 512 / best / 1e3, bb * 1e3, 8192 / bb / 1e3))
+'''
+
+libs = sys.argv[1:] or [None]
+for rnd in range(2):
+    for lib in libs:
+        env = dict(os.environ)
+        if lib:
+            env['SCFEAT_LIB'] = os.path.abspath(lib)
+        subprocess.run([sys.executable, '-c', CHILD], env=env, check=False)
