@@ -190,6 +190,33 @@ def test_audio_to_feature_crop_pad_and_ragged_batch(example_pcm):
     assert_cepstrum_close(scfeat.data_utils.vectorize_raw(a[:5000]), opipe.vectorize_raw(a[:5000], p))
 
 
+def test_silent_frame_next_to_loud_frame(example_pcm):
+    """An exactly-zero frame (front padding) that shares an FFT with a loud frame must still come out as the
+    reference's floor value ln(eps) in every band: the two-for-one FFT may not leak its partner into it."""
+    _, pcm = example_pcm
+    p = opipe.Params()
+    rng = np.random.default_rng(11)
+    loud = rng.integers(-32768, 32768, size=16000, dtype=np.int16)
+    for n in (1500, 2012, 2524, 9000, 9512):             # both parities of the first non-silent frame
+        for src in (pcm[4], loud):
+            x = src[:n]
+            want = opipe.audio_to_feature(audio_of(x), p)
+            got = scfeat.data_utils.audio_to_feature(x)                       # int16, front pad in the kernel
+            assert_cepstrum_close(got, want)
+            gotf = scfeat.data_utils.audio_to_feature(audio_of(x))           # float path
+            assert_cepstrum_close(gotf, want)
+            silent = np.flatnonzero(np.abs(want[:, 1:]).max(axis=1) < 1e-9)
+            assert len(silent) > 0
+            np.testing.assert_allclose(got[silent, 0], -36.04365339, atol=2e-5)
+    # same through the fast path: zeros written into a full-length clip, log-mel bands too
+    clip = np.zeros(16000, dtype=np.int16)
+    clip[14336:] = loud[:1664]                                               # frames 0..26 silent, 27.. loud
+    got = scfeat.sonopy.mel_spec(clip, 16000, (1024, 512), 1024, 20)
+    want = osonopy.mel_spec(audio_of(clip), 16000, (1024, 512), 1024, 20)
+    assert_log_close(got, want)
+    np.testing.assert_allclose(got[:27], -36.04365339, atol=2e-5)
+
+
 def test_use_delta_and_changed_pr(example_pcm):
     _, pcm = example_pcm
     pr = scfeat.params.pr

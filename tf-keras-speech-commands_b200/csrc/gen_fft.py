@@ -69,6 +69,36 @@ def emit_fft(n):
     return '\n'.join(out)
 
 
+def emit_fft_tw(n):
+    """Variant whose first stage also applies per-element input twiddles (the inter-pass twiddles of a two-pass
+    FFT): x = z * c before the butterfly.  Fused form per first-stage butterfly (a = z[n]*c[n], b = z[m]*c[m]):
+        p   = z[n] * c[n]                      2 FMUL + 2 FFMA
+        a'  = p + z[m] * c[m]                  4 FFMA
+        b'  = 2p - a'                          2 FFMA         -> 10 instead of 8 + 4."""
+    bits = n.bit_length() - 1
+    body = emit_fft(n).split('\n')
+    start = next(i for i, l in enumerate(body) if 'stage span=1' in l)
+    end = next(i for i, l in enumerate(body) if 'stage span=2' in l)
+    out = []
+    out.append('// %d-point complex FFT with fused input twiddles: computes FFT of z[n] * c[n].' % n)
+    out.append('// In: zr/zi/cr/ci in NATURAL order.  Out: xr/xi[k] = Z[k] in natural order.')
+    out.append('__device__ __forceinline__ void fft%d_dit_tw(const float (&zr)[%d], const float (&zi)[%d], const float (&cr)[%d],' % (n, n, n, n))
+    out.append('                                             const float (&ci)[%d], float (&xr)[%d], float (&xi)[%d])' % (n, n, n))
+    out.append('{')
+    out.append('    float ar, ai, br, bi;')
+    out.append('    float pr, pi;')
+    out.append('    // ---- stage span=1 fused with the input twiddles')
+    for i in range(0, n, 2):
+        na, nb = bitrev(i, bits), bitrev(i + 1, bits)
+        out.append('    pr = __fmaf_rn(zr[%d], cr[%d], -zi[%d] * ci[%d]); pi = __fmaf_rn(zr[%d], ci[%d], zi[%d] * cr[%d]);'
+                   % (na, na, na, na, na, na, na, na))
+        out.append('    xr[%d] = __fmaf_rn(zr[%d], cr[%d], __fmaf_rn(-zi[%d], ci[%d], pr)); xi[%d] = __fmaf_rn(zr[%d], ci[%d], __fmaf_rn(zi[%d], cr[%d], pi));'
+                   % (i, nb, nb, nb, nb, i, nb, nb, nb, nb))
+        out.append('    xr[%d] = __fmaf_rn(2.0f, pr, -xr[%d]); xi[%d] = __fmaf_rn(2.0f, pi, -xi[%d]);' % (i + 1, i, i + 1, i))
+    out += body[end:]
+    return '\n'.join(out)
+
+
 def main():
     print('// GENERATED by gen_fft.py -- do not edit.  See that file for the derivation.')
     print('#pragma once')
@@ -84,6 +114,8 @@ def main():
     for n in (8, 16, 32):
         print(emit_fft(n))
         print()
+    print(emit_fft_tw(32))
+    print()
 
 
 if __name__ == '__main__':

@@ -404,7 +404,9 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         std::vector<double> bank;
         build_bank(cfg, bank);
         const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
-        build_tasks(bank, cfg->n_filt, p->n_bins, cep, bank_groups(p->radix_r), tl);
+        // the frame energy is always computed: the cepstrum needs it as c0, and the fast int16 path derives its
+        // "frame is all zero" decision from it (scfeat_kernels.cu)
+        build_tasks(bank, cfg->n_filt, p->n_bins, true, bank_groups(p->radix_r), tl);
         p->n_tasks = (int)tl.words.size();
         p->n_q = (int)tl.qspec.size();
         p->n_dst = tl.n_dst;
@@ -484,6 +486,10 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.out_cols = plan->out_cols;
     kp.out_kind = c.output;
     kp.power_scale = is_f32 ? plan->power_scale_f32 : plan->power_scale_i16;
+    {   // smallest non-zero int16 frame: one sample of +-1 -> energy 513/1024 * pcm_scale^2
+        const double pcm = (c.pcm_scale > 0.f) ? (double)c.pcm_scale : 1.0 / 32768.0;
+        kp.zero_energy = is_f32 ? 0.f : (float)(0.25 * pcm * pcm);
+    }
     kp.tables = is_f32 ? plan->d_tab_f32 : plan->d_tab_i16;
     kp.table_bytes = plan->table_bytes;
     kp.off_wts = plan->off_wts;

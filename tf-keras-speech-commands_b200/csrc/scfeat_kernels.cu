@@ -25,11 +25,8 @@
 
 namespace scf {
 
-#ifndef SCF_PREFETCH_IN_MIRROR
-#define SCF_PREFETCH_IN_MIRROR 1
-#endif
-#ifndef SCF_BANK_PAIRS
-#define SCF_BANK_PAIRS 1
+#ifndef SCF_MIN_CTAS
+#define SCF_MIN_CTAS kCtasPerSm
 #endif
 
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
@@ -55,6 +52,9 @@ struct Geo {
 
 __device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
 __device__ __forceinline__ float to_f32(float v) { return v; }
+// bits that are set iff the sample is not zero (-0.0f counts as zero)
+__device__ __forceinline__ uint32_t nz_bits(int16_t v) { return (uint32_t)(uint16_t)v; }
+__device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
 template <int R>
 __device__ __forceinline__ void fft_r(float (&xr)[R], float (&xi)[R])
@@ -88,9 +88,10 @@ __device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
 
 // Generic loader: any window / hop / per-clip length / pre-emphasis / window function.
 template <int R, typename InT>
-__device__ __forceinline__ void load_frame_generic(const KParams& p, const InT* __restrict__ clip_base,
-                                                   const ClipGeom& cg, int frame, int lane, float (&dst)[R])
+__device__ __forceinline__ uint32_t load_frame_generic(const KParams& p, const InT* __restrict__ clip_base,
+                                                       const ClipGeom& cg, int frame, int lane, float (&dst)[R])
 {
+    uint32_t nz = 0;
     const bool valid = frame < cg.n_frames;
     const int64_t s0 = (int64_t)frame * p.hop - cg.pad;     // index of sample n = 0 in the clip's own data
 #pragma unroll
@@ -106,8 +107,10 @@ __device__ __forceinline__ void load_frame_generic(const KParams& p, const InT* 
             }
             if (p.win != nullptr) v *= __ldg(p.win + n);
         }
+        nz |= nz_bits(v);
         dst[i] = v;
     }
+    return nz;
 }
 
 // ---- small PTX helpers: mbarrier + TMA 1-D bulk copy (tables -> shared memory) -----------------------
@@ -154,7 +157,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
 }
 
 template <int R, typename InT, bool FAST>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KParams p, const uint32_t n_tiles)
+__global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const KParams p, const uint32_t n_tiles)
 {
     using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
@@ -214,6 +217,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
         prow_slot = s_xch + sw * geo::XWARP + geo::P_OFF + 4 * ((2 * geo::G * sw) & 7) + ls * geo::PROW;
     }
 
+    // How exactly-zero frames are recognised (they must produce exactly zero power, see the FFT stage):
+    //  * fast int16 path with a bank: from the frame energy in the epilogue -- a non-zero int16 frame has raw
+    //    energy >= 0.5 while its partner can leak at most ~2e-3 into it, so energy < 0.25 means "all zero";
+    //  * everything else (float input, generic loader, power output): bitwise OR of the samples + warp vote.
+    constexpr bool kEnergyZero = FAST && sizeof(InT) == 2;
+    const bool bit_detect = !kEnergyZero || p.out_kind == SCF_OUT_POWER;
     const InT* __restrict__ in = reinterpret_cast<const InT*>(p.in);
     const uint32_t ppc = (uint32_t)p.pairs_per_clip;
     const uint32_t n_pairs = (uint32_t)p.n_pairs;
@@ -249,12 +258,28 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
         // =========================== FFT stage (per warp) =======================================
         if (pair0 + warp * geo::G < n_pairs) {
             // ---- pass 1: lane = n2; R-point FFT over n1 of z[n2 + 32 n1], z = A + iB ----------------
+            // A frame whose samples are ALL exactly zero (front padding, digital silence) must come out as exactly
+            // zero power: the two-for-one separation below would otherwise leak ~4e-15 of its partner's energy into
+            // it, which is visible above the eps floor of the log.  zero_mask: bit 2g = frame A of pair g, 2g+1 = B.
+            uint32_t zero_mask = 0;
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
                 const uint32_t gp = pair0 + warp * geo::G + g;
                 if (gp < n_pairs) {
                     float xr[R], xi[R];
+                    uint32_t nz_a = 0, nz_b = 0;
                     if constexpr (FAST) {
+                        if (bit_detect) {
+                            uint32_t o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+                            for (int j = 0; j < R / 2; ++j) {
+                                o0 |= nz_bits(raw[g][j]);
+                                o1 |= nz_bits(raw[g][j + R / 2]);
+                                o2 |= nz_bits(raw[g][j + R]);
+                            }
+                            nz_a = o0 | o1;
+                            nz_b = o1 | o2;
+                        }
                         // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half their
                         // samples; raw[g][j] = x[n_fft*q + lane + 32 j], j < R + R/2 (zeros where frame B is absent)
 #pragma unroll
@@ -269,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                             if ((int)(2 * q + 1) >= p.frames_per_clip) {          // frame B absent (odd frame count)
 #pragma unroll
                                 for (int i = 0; i < R; ++i) xi[i] = 0.f;
+                                nz_b = 0;
                             }
                         }
                     } else {
@@ -276,8 +302,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                         const int q = (int)(gp - clip * ppc);
                         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
-                        load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
-                        load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
+                        nz_a = load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
+                        nz_b = load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
+                    }
+                    if (bit_detect) {
+                        if (!__any_sync(0xffffffffu, nz_a != 0)) zero_mask |= 1u << (2 * g);
+                        if (!__any_sync(0xffffffffu, nz_b != 0)) zero_mask |= 1u << (2 * g + 1);
                     }
                     fft_r<R>(xr, xi);
                     float4* row = reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW);
@@ -295,20 +325,20 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
             float yr[32], yi[32];
             {
                 const float* col = xw + g2 * geo::XPAIR + 2 * k1;
+                // the inter-pass twiddles are folded into the first butterfly stage (10 instead of 12 FP32
+                // instructions per butterfly, see gen_fft.py)
+                float zr[32], zi[32], cr[32], ci[32];
 #pragma unroll
                 for (int n2 = 0; n2 < 32; n2 += 2) {
                     const float4 t = s_tw4[(n2 / 2) * 32 + lane];
                     const float2 a = *reinterpret_cast<const float2*>(col + n2 * geo::XROW);
                     const float2 b = *reinterpret_cast<const float2*>(col + (n2 + 1) * geo::XROW);
-                    const int ia = scf_bitrev(n2, 5), ib = scf_bitrev(n2 + 1, 5);
-                    yr[ia] = __fmaf_rn(a.x, t.x, -a.y * t.y);
-                    yi[ia] = __fmaf_rn(a.x, t.y, a.y * t.x);
-                    yr[ib] = __fmaf_rn(b.x, t.z, -b.y * t.w);
-                    yi[ib] = __fmaf_rn(b.x, t.w, b.y * t.z);
+                    zr[n2] = a.x; zi[n2] = a.y; zr[n2 + 1] = b.x; zi[n2 + 1] = b.y;
+                    cr[n2] = t.x; ci[n2] = t.y; cr[n2 + 1] = t.z; ci[n2 + 1] = t.w;
                 }
+                fft32_dit_tw(zr, zi, cr, ci, yr, yi);
             }
             __syncwarp();    // every lane has read its column: the region may now be reused
-            fft32_dit(yr, yi);
 
             // ---- separate the two frames: upper half of Z through shared memory ---------------------
             float2* mir = reinterpret_cast<float2*>(xw + g2 * geo::MIR);
@@ -316,10 +346,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
             for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = make_float2(yr[k2], yi[k2]);
             mir[k1 == 0 ? geo::NB : geo::NB + 1] = make_float2(yr[0], yi[0]);      // Z[N] == Z[0]; NB+1 is a dump slot
             __syncwarp();
-#if SCF_PREFETCH_IN_MIRROR
             // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
             if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-#endif
             float* pa_row = pw + (2 * g2) * geo::PROW;
             float* pb_row = pa_row + geo::PROW;
 #pragma unroll
@@ -335,9 +363,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                 pa_row[geo::NB] = 4.f * yr[16] * yr[16];
                 pb_row[geo::NB] = 4.f * yi[16] * yi[16];
             }
-#if !SCF_PREFETCH_IN_MIRROR
-            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-#endif
+            if (__builtin_expect(zero_mask != 0, 0)) {                     // rare: exact zeros for silent frames
+                const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
+#pragma unroll 1
+                for (int k = k1; k <= geo::NB; k += R) {                   // a real loop: keep the hot path short
+                    if (za) pa_row[k] = 0.f;
+                    if (zb) pb_row[k] = 0.f;
+                }
+            }
         } else {
             if (!tables_ready) {
                 mbar_wait(s_bar, 0);
@@ -392,7 +425,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
         // registers and the task flagged `last` stores the run's partial sum.  Every group's list is padded to an
         // even length (null tasks: zero weights), two tasks are in flight per iteration and the next pair of task
         // words is fetched one iteration ahead, so the shared-memory round trips overlap the FMAs.
-#if SCF_BANK_PAIRS
         {
             const int t_end = s_tbeg[grp + 1];
             int t = s_tbeg[grp];
@@ -434,37 +466,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) extract_kernel(const KPa
                 }
             }
         }
-#else
-        {
-            const int t_end = s_tbeg[grp + 1];
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-            for (int t = s_tbeg[grp]; t < t_end; ++t) {
-                const uint32_t tk = s_tasks[t];
-                const float4* pp = reinterpret_cast<const float4*>(prow_slot + (tk & 0xfffu));
-                const float4* ww = s_wts4 + 4 * t;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 a = pp[i];
-                    const float4 w = ww[i];
-                    acc0 = __fmaf_rn(a.x, w.x, acc0);
-                    acc1 = __fmaf_rn(a.y, w.y, acc1);
-                    acc2 = __fmaf_rn(a.z, w.z, acc2);
-                    acc3 = __fmaf_rn(a.w, w.w, acc3);
-                }
-                if (tk & 0x80000000u) {
-                    s_part[((tk >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
-                    acc0 = acc1 = acc2 = acc3 = 0.f;
-                }
-            }
-        }
-#endif
         __syncthreads();
 
         // =========================== log ========================================================
-        for (int q = grp; q < p.n_q; q += geo::NGRP) {
+        bool silent = false;
+        if constexpr (kEnergyZero) {
+            const int2 qe = s_qspec[p.n_filt];                 // the frame-energy quantity is always the last one
+            float e = s_part[qe.x * geo::SLOTS + slot];
+            for (int j = 1; j < qe.y; ++j) e += s_part[(qe.x + j) * geo::SLOTS + slot];
+            silent = e < p.zero_energy;
+        }
+        const int n_q_out = (p.out_kind == SCF_OUT_LOG_BANK) ? p.n_filt : p.n_q;
+        for (int q = grp; q < n_q_out; q += geo::NGRP) {
             const int2 qs = s_qspec[q];
             float v = s_part[qs.x * geo::SLOTS + slot];
             for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
+            if (silent) v = 0.f;
             const float lv = __logf(fmaxf(v, SCF_EPS));          // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
             if (p.out_kind == SCF_OUT_LOG_BANK) {
                 if (out_row >= 0) {
@@ -551,7 +568,11 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
         if (e != cudaSuccess) return e;
         configured[dev & 15] = smem;
     }
+#ifdef SCF_GRID_CTAS
+    int64_t grid = (int64_t)num_sms * SCF_GRID_CTAS;
+#else
     int64_t grid = (int64_t)num_sms * kCtasPerSm;
+#endif
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};
