@@ -99,6 +99,60 @@ def emit_fft_tw(n):
     return '\n'.join(out)
 
 
+def emit_fft_packed(n, with_tw=False):
+    """Packed (f32x2) form: x[i] is a 64-bit (re, im) pair.  Butterflies (a' = a + w b, b' = a - w b):
+        w = 1      a' = add2(a, b); b' = sub2(a, b)                                     2 instructions
+        w = -i     t = (b.im, -b.re) [operand modifiers]; a' = add2(a, t); b' = sub2(a, t)   2
+        general    a' = fma2(b, wr, a); a' = fma2(i*b, wi, a'); b' = fma2(2, a, -a')   (i*b = (-b.im, b.re) is an operand modifier)   3
+    i.e. half the issue slots of the scalar form with identical rounding.
+    with_tw: the first stage also multiplies its inputs by per-element twiddles c (natural order arrays z, c):
+        p = mul2(z_a, cr); p = fma2(i*z_a, ci, p); a' = fma2(z_b, dr, p); a' = fma2(i*z_b, di, a'); b' = fma2(2, p, -a')
+                                                                                        5 instead of 10."""
+    bits = n.bit_length() - 1
+    out = []
+    name = 'fft%d_p2%s' % (n, '_tw' if with_tw else '')
+    if with_tw:
+        out.append('// %d-point complex FFT of z[n] * c[n], packed f32x2.  In: z, c natural order.  Out: x natural order.' % n)
+        out.append('__device__ __forceinline__ void %s(const f2 (&z)[%d], const f2 (&c)[%d], f2 (&x)[%d])' % (name, n, n, n))
+    else:
+        out.append('// %d-point complex FFT, packed f32x2, in place.  In: x[i] = z[bitrev(i)].  Out: x[k] = Z[k].' % n)
+        out.append('__device__ __forceinline__ void %s(f2 (&x)[%d])' % (name, n))
+    out.append('{')
+    out.append('    f2 a, b, t;')
+    count = 0
+    span = 1
+    first = True
+    while span < n:
+        out.append('    // ---- stage span=%d' % span)
+        for g in range(0, n, 2 * span):
+            for k in range(span):
+                i, j = g + k, g + k + span
+                if first and with_tw:
+                    na, nb = bitrev(i, bits), bitrev(j, bits)
+                    out.append('    t = mul2(z[%d], bc(lo(c[%d]))); t = fma2(mul_i(z[%d]), bc(hi(c[%d])), t);' % (na, na, na, na))
+                    out.append('    a = fma2(z[%d], bc(lo(c[%d])), t); a = fma2(mul_i(z[%d]), bc(hi(c[%d])), a);' % (nb, nb, nb, nb))
+                    out.append('    x[%d] = a; x[%d] = fma2(pk(2.0f, 2.0f), t, neg2(a));' % (i, j))
+                    count += 5
+                elif k == 0:
+                    out.append('    a = x[%d]; b = x[%d]; x[%d] = add2(a, b); x[%d] = sub2(a, b);' % (i, j, i, j))
+                    count += 2
+                elif 2 * k == span:
+                    out.append('    a = x[%d]; t = mul_mi(x[%d]); x[%d] = add2(a, t); x[%d] = sub2(a, t);' % (i, j, i, j))
+                    count += 2
+                else:
+                    ang = -2.0 * math.pi * k / (2 * span)
+                    wr, wi = math.cos(ang), math.sin(ang)
+                    out.append('    a = x[%d]; b = x[%d]; t = fma2(b, bc(%s), a); t = fma2(mul_i(b), bc(%s), t);'
+                               % (i, j, lit(wr), lit(wi)))
+                    out.append('    x[%d] = t; x[%d] = fma2(pk(2.0f, 2.0f), a, neg2(t));' % (i, j))
+                    count += 3
+        span *= 2
+        first = False
+    out.append('}')
+    out.insert(2 if not with_tw else 2, '// %d packed instructions' % count)
+    return '\n'.join(out)
+
+
 def main():
     print('// GENERATED by gen_fft.py -- do not edit.  See that file for the derivation.')
     print('#pragma once')
@@ -115,6 +169,13 @@ def main():
         print(emit_fft(n))
         print()
     print(emit_fft_tw(32))
+    print()
+    print('#include "f32x2.cuh"')
+    print()
+    for n in (8, 16, 32):
+        print(emit_fft_packed(n))
+        print()
+    print(emit_fft_packed(32, with_tw=True))
     print()
 
 

@@ -57,11 +57,11 @@ __device__ __forceinline__ uint32_t nz_bits(int16_t v) { return (uint32_t)(uint1
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
 template <int R>
-__device__ __forceinline__ void fft_r(float (&xr)[R], float (&xi)[R])
+__device__ __forceinline__ void fft_r(f2 (&x)[R])
 {
-    if constexpr (R == 32) fft32_dit(xr, xi);
-    else if constexpr (R == 16) fft16_dit(xr, xi);
-    else fft8_dit(xr, xi);
+    if constexpr (R == 32) fft32_p2(x);
+    else if constexpr (R == 16) fft16_p2(x);
+    else fft8_p2(x);
 }
 
 struct ClipGeom {
@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
 
     // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
     // of the current tile run (those need few registers), so the FFT stage never waits on HBM
+    // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead)
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2;
     InT raw[geo::G][geo::NLOAD];
     auto prefetch = [&](uint32_t tile) {
-        if constexpr (FAST) {
+        if constexpr (kPrefetch) {
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
                 const uint32_t gp = tile * geo::PPT + warp * geo::G + g;
@@ -266,9 +268,19 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             for (int g = 0; g < geo::G; ++g) {
                 const uint32_t gp = pair0 + warp * geo::G + g;
                 if (gp < n_pairs) {
-                    float xr[R], xi[R];
+                    f2 x[R];                                   // (re, im) = (frame A sample, frame B sample), packed
                     uint32_t nz_a = 0, nz_b = 0;
                     if constexpr (FAST) {
+                        if constexpr (!kPrefetch) {            // load now: raw[g][j] = x[n_fft*q + lane + 32 j]
+                            const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
+                            const uint32_t q = gp - clip * ppc;
+                            const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
+                            const bool b_ok = (int)(2 * q + 1) < p.frames_per_clip;
+#pragma unroll
+                            for (int j = 0; j < R; ++j) raw[g][j] = __ldg(src + 32 * j);
+#pragma unroll
+                            for (int j = R; j < geo::NLOAD; ++j) raw[g][j] = b_ok ? __ldg(src + 32 * j) : (InT)0;
+                        }
                         if (bit_detect) {
                             uint32_t o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
@@ -282,37 +294,37 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                         }
                         // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half their
                         // samples; raw[g][j] = x[n_fft*q + lane + 32 j], j < R + R/2 (zeros where frame B is absent)
-#pragma unroll
-                        for (int i = 0; i < R; ++i) {
-                            const int n1 = scf_bitrev(i, geo::LOG2R);
-                            xr[i] = to_f32(raw[g][n1]);
-                            xi[i] = to_f32(raw[g][n1 + R / 2]);
-                        }
+                        bool b_absent = false;
                         if (p.frames_per_clip & 1) {
                             const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
                             const uint32_t q = gp - clip * ppc;
-                            if ((int)(2 * q + 1) >= p.frames_per_clip) {          // frame B absent (odd frame count)
+                            b_absent = (int)(2 * q + 1) >= p.frames_per_clip;      // odd frame count: last pair
+                        }
+                        if (b_absent) nz_b = 0;
 #pragma unroll
-                                for (int i = 0; i < R; ++i) xi[i] = 0.f;
-                                nz_b = 0;
-                            }
+                        for (int i = 0; i < R; ++i) {
+                            const int n1 = scf_bitrev(i, geo::LOG2R);
+                            x[i] = pk(to_f32(raw[g][n1]), b_absent ? 0.f : to_f32(raw[g][n1 + R / 2]));
                         }
                     } else {
                         const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
                         const int q = (int)(gp - clip * ppc);
                         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
+                        float xr[R], xi[R];
                         nz_a = load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
                         nz_b = load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
+#pragma unroll
+                        for (int i = 0; i < R; ++i) x[i] = pk(xr[i], xi[i]);
                     }
                     if (bit_detect) {
                         if (!__any_sync(0xffffffffu, nz_a != 0)) zero_mask |= 1u << (2 * g);
                         if (!__any_sync(0xffffffffu, nz_b != 0)) zero_mask |= 1u << (2 * g + 1);
                     }
-                    fft_r<R>(xr, xi);
-                    float4* row = reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW);
+                    fft_r<R>(x);
+                    ulonglong2* row = reinterpret_cast<ulonglong2*>(xw + g * geo::XPAIR + lane * geo::XROW);
 #pragma unroll
-                    for (int k = 0; k < R; k += 2) row[k / 2] = make_float4(xr[k], xi[k], xr[k + 1], xi[k + 1]);
+                    for (int k = 0; k < R; k += 2) row[k / 2] = make_ulonglong2(x[k], x[k + 1]);
                 }
             }
             __syncwarp();
@@ -322,29 +334,28 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             }
 
             // ---- pass 2: lane = (pair g2, column k1); twiddle, 32-point FFT over n2 -> Z[k1 + R k2] --
-            float yr[32], yi[32];
+            // (the inter-pass twiddles are folded into the first butterfly stage, see gen_fft.py)
+            f2 y[32];
             {
                 const float* col = xw + g2 * geo::XPAIR + 2 * k1;
-                // the inter-pass twiddles are folded into the first butterfly stage (10 instead of 12 FP32
-                // instructions per butterfly, see gen_fft.py)
-                float zr[32], zi[32], cr[32], ci[32];
+                f2 z[32], c[32];
 #pragma unroll
                 for (int n2 = 0; n2 < 32; n2 += 2) {
-                    const float4 t = s_tw4[(n2 / 2) * 32 + lane];
-                    const float2 a = *reinterpret_cast<const float2*>(col + n2 * geo::XROW);
-                    const float2 b = *reinterpret_cast<const float2*>(col + (n2 + 1) * geo::XROW);
-                    zr[n2] = a.x; zi[n2] = a.y; zr[n2 + 1] = b.x; zi[n2 + 1] = b.y;
-                    cr[n2] = t.x; ci[n2] = t.y; cr[n2 + 1] = t.z; ci[n2 + 1] = t.w;
+                    const ulonglong2 t = reinterpret_cast<const ulonglong2*>(s_tw4)[(n2 / 2) * 32 + lane];
+                    z[n2] = *reinterpret_cast<const f2*>(col + n2 * geo::XROW);
+                    z[n2 + 1] = *reinterpret_cast<const f2*>(col + (n2 + 1) * geo::XROW);
+                    c[n2] = t.x;
+                    c[n2 + 1] = t.y;
                 }
-                fft32_dit_tw(zr, zi, cr, ci, yr, yi);
+                fft32_p2_tw(z, c, y);
             }
             __syncwarp();    // every lane has read its column: the region may now be reused
 
             // ---- separate the two frames: upper half of Z through shared memory ---------------------
-            float2* mir = reinterpret_cast<float2*>(xw + g2 * geo::MIR);
+            f2* mir = reinterpret_cast<f2*>(xw + g2 * geo::MIR);
 #pragma unroll
-            for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = make_float2(yr[k2], yi[k2]);
-            mir[k1 == 0 ? geo::NB : geo::NB + 1] = make_float2(yr[0], yi[0]);      // Z[N] == Z[0]; NB+1 is a dump slot
+            for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = y[k2];
+            mir[k1 == 0 ? geo::NB : geo::NB + 1] = y[0];                            // Z[N] == Z[0]; NB+1 is a dump slot
             __syncwarp();
             // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
             if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
@@ -353,15 +364,18 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
                 const int k = k1 + R * k2;
-                const float2 m = mir[geo::NB - k];                         // Z[N - k]
-                const float sr = yr[k2] + m.x, dr = yi[k2] - m.y;          // 2 A[k]
-                const float si = yi[k2] + m.y, di = m.x - yr[k2];          // 2 B[k]
-                pa_row[k] = __fmaf_rn(sr, sr, dr * dr);
-                pb_row[k] = __fmaf_rn(si, si, di * di);
+                const f2 m = mir[geo::NB - k];                                       // Z[N - k]
+                // 2A[k] = Z + conj(Zm) = (yr + mr, yi - mi);  2B[k] = (yi + mi, mr - yr)
+                const f2 u1 = add2(y[k2], m);                                        // (yr + mr, yi + mi) = (Re 2A, Re 2B)
+                const f2 u2 = add2(mul_mi(y[k2]), mul_i(m));                         // (yi - mi, mr - yr) = (Im 2A, Im 2B)
+                const f2 pp = fma2(u2, u2, mul2(u1, u1));                            // (|2A|^2, |2B|^2)
+                pa_row[k] = lo(pp);
+                pb_row[k] = hi(pp);
             }
-            if (k1 == 0) {                                                 // bin n_fft/2 mirrors onto itself
-                pa_row[geo::NB] = 4.f * yr[16] * yr[16];
-                pb_row[geo::NB] = 4.f * yi[16] * yi[16];
+            if (k1 == 0) {                                                           // bin n_fft/2 mirrors onto itself
+                const f2 pp = mul2(mul2(y[16], y[16]), bc(4.f));
+                pa_row[geo::NB] = lo(pp);
+                pb_row[geo::NB] = hi(pp);
             }
             if (__builtin_expect(zero_mask != 0, 0)) {                     // rare: exact zeros for silent frames
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
