@@ -421,7 +421,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         }
     }
     auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t sz_tw = 16 * 32 * sizeof(float4);
+    const size_t sz_tw = 8 * 32 * sizeof(float4) + 32 * sizeof(float2);    // W^(k1 n2), n2 < 16, then W^(16 k1)
     p->off_wts = (int)sz_tw;
     p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
     p->off_tasks = (int)align16(p->off_dct + dct_t.size() * 4);
@@ -435,13 +435,18 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         {
             const int R = p->radix_r, N = cfg->n_fft;
             float4* tw = reinterpret_cast<float4*>(blob.data());
-            for (int jj = 0; jj < 16; ++jj)
+            for (int jj = 0; jj < 8; ++jj)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int k1 = lane % R;
                     const double a0 = -2.0 * M_PI * (double)((k1 * (2 * jj)) % N) / N;
                     const double a1 = -2.0 * M_PI * (double)((k1 * (2 * jj + 1)) % N) / N;
                     tw[jj * 32 + lane] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
                 }
+            float2* w16 = reinterpret_cast<float2*>(tw + 8 * 32);
+            for (int lane = 0; lane < 32; ++lane) {
+                const double a = -2.0 * M_PI * (double)(((lane % R) * 16) % N) / N;
+                w16[lane] = make_float2((float)cos(a), (float)sin(a));
+            }
         }
         float* w = reinterpret_cast<float*>(blob.data() + p->off_wts);
         for (size_t i = 0; i < tl.weights.size(); ++i) w[i] = (float)(tl.weights[i] * ps);
@@ -539,7 +544,7 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
     DeviceGuard guard(plan->device);
     if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
     const size_t smem = extract_smem_bytes(plan->radix_r, kp);
-    if (smem > (size_t)(227 * 1024) / kCtasPerSm - 1024) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
+    if (smem > extract_smem_limit(plan->radix_r, kp)) return fail(SCF_ERR_INVALID, "configuration needs too much shared memory");
     // the kernel indexes pairs with 32 bits: very large jobs go out as several launches
     const int ppt = pairs_per_tile(plan->radix_r);
     const int64_t max_clips = std::max<int64_t>(1, (0x7fffffffLL - ppt) / std::max(1, kp.pairs_per_clip));

@@ -74,6 +74,7 @@ struct LaunchGeom {
 cudaError_t launch_extract(int radix_r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles,
                            int num_sms, cudaStream_t st, size_t smem_bytes);
 size_t extract_smem_bytes(int radix_r, const KParams& p);
+size_t extract_smem_limit(int radix_r, const KParams& p);
 int pairs_per_tile(int radix_r);
 int bank_groups(int radix_r);
 cudaError_t prepare_kernels(int device);

@@ -19,6 +19,7 @@
 //    the same rows are stored to every peer GPU's cache (fused all-gather over NVLink).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fft_gen.cuh"
 #include "scfeat_internal.h"
@@ -31,23 +32,28 @@ namespace scf {
 
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
 
-template <int R>
+// SWZ = false: exchange rows are padded by 16 bytes (conflict-free without address arithmetic), the power rows sit
+//               behind the mirror buffers; 8704 bytes per warp at n_fft = 1024.
+// SWZ = true : exchange rows are unpadded and XOR-swizzled at float4 granularity, the power rows reuse the mirror
+//               buffers' space; exactly 8192 bytes per warp, which lets 24 warps share one SM (see TEAMS).
+template <int R, bool SWZ = false>
 struct Geo {
     static constexpr int NFFT = 32 * R;
     static constexpr int NB = 16 * R;                 // highest bin index (n_fft / 2)
     static constexpr int LOG2R = (R == 32) ? 5 : (R == 16) ? 4 : 3;
     static constexpr int G = 32 / R;                  // frame pairs per warp
-    static constexpr int PPT = kWarps * G;            // pairs per tile
+    static constexpr int PPT = kWarps * G;            // pairs per tile (one tile = one team's 8 warps)
     static constexpr int SLOTS = 2 * PPT;             // frame slots per tile
     static constexpr int NGRP = kThreads / SLOTS;     // bank-phase thread groups
-    static constexpr int XROW = 2 * R + 4;            // floats per exchange row (16 B pad -> conflict-free float4 rows)
+    static constexpr int XROW = SWZ ? 2 * R : 2 * R + 4;   // floats per exchange row
     static constexpr int XPAIR = 32 * XROW;
     static constexpr int XWARP = G * XPAIR;           // floats of shared memory owned by one warp
     static constexpr int MIR = 2 * NB + 4;            // floats per pair: upper half of Z (+1 slot for Z[0])
     static constexpr int PROW = NB + 4;               // floats per power row ( = 4 mod 32 -> conflict-free float4 columns)
-    static constexpr int P_OFF = G * MIR;             // power rows start behind the mirror buffers
+    static constexpr int P_OFF = SWZ ? 0 : G * MIR;   // power rows: behind the mirror buffers, or on top of them
     static constexpr int NLOAD = R + R / 2;           // fast path: strided samples per lane covering both frames
-    static_assert(P_OFF + 2 * G * PROW + 32 <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(P_OFF + 2 * G * PROW + 32 <= XWARP && G * MIR <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(!SWZ || R == 32, "the swizzled layout is written for n_fft = 1024");
 };
 
 __device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
@@ -156,30 +162,42 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
     return (t + ((n - t) >> 1)) >> shift;
 }
 
-template <int R, typename InT, bool FAST>
-__global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const KParams p, const uint32_t n_tiles)
+// TEAMS = 1: a CTA is one team of 8 warps (256 threads); two CTAs per SM (128 registers per thread).
+// TEAMS = 3: a CTA is three independent teams of 8 warps that share ONE copy of the tables and synchronise through
+//            their own named barriers: 24 warps per SM at 80 registers per thread (the packed FFT fits), which is
+//            what hides the FFMA2 / LDS latencies.  Needs the swizzled 8 KB-per-warp layout.
+template <int R, typename InT, bool FAST, int TEAMS>
+__global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1)
+    extract_kernel(const KParams p, const uint32_t n_tiles)
 {
-    using geo = Geo<R>;
+    constexpr bool SWZ = TEAMS > 1;
+    using geo = Geo<R, SWZ>;
     extern __shared__ __align__(16) float smem[];
 
+    const int tid = threadIdx.x % kThreads;          // thread within its team
+    const int team = threadIdx.x / kThreads;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;                       // warp within its team
+
     // ---- shared memory carve-up (must match extract_smem_bytes; the table part mirrors the plan's blob) ----
-    float* s_xch = smem;
-    unsigned char* s_tab = reinterpret_cast<unsigned char*>(s_xch + kWarps * geo::XWARP);
+    float* s_xch = smem + team * (kWarps * geo::XWARP);
+    unsigned char* s_tab = reinterpret_cast<unsigned char*>(smem + TEAMS * kWarps * geo::XWARP);
     const float4* s_tw4 = reinterpret_cast<const float4*>(s_tab);
     const float4* s_wts4 = reinterpret_cast<const float4*>(s_tab + p.off_wts);
     const float* s_dct = reinterpret_cast<const float*>(s_tab + p.off_dct);
     const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
-    float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes);
-    float* s_logq = s_part + p.n_dst * geo::SLOTS;
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_logq + n_lq * geo::SLOTS);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int team_floats = (p.n_dst + n_lq) * geo::SLOTS;
+    float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes) + team * team_floats;
+    float* s_logq = s_part + p.n_dst * geo::SLOTS;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + p.table_bytes) + TEAMS * team_floats);
     float* xw = s_xch + warp * geo::XWARP;
+    auto team_sync = [&]() {
+        if constexpr (TEAMS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kThreads) : "memory");
+    };
 
     // Programmatic dependent launch: let the NEXT extract launch of the stream start filling SMs as soon as
     // this grid's CTAs retire (its loads / FFTs do not depend on us).  Every extract grid waits for its
@@ -190,15 +208,21 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
 
     // ---- one-time per CTA -----------------------------------------------------------------------------------
     // tables: ONE TMA bulk copy, waited for just before the first pass 2 (overlaps the first loads + pass 1)
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
         bulk_g2s(s_tab, p.tables, (uint32_t)p.table_bytes, s_bar);
     }
-    // the 16-byte pad of every exchange row is never written by pass 1 but aliases power-row words that the
-    // bank phase multiplies by zero weights: it must not hold NaN bit patterns
+    if constexpr (!SWZ) {
+        // the 16-byte pad of every exchange row is never written by pass 1 but aliases power-row words that the
+        // bank phase multiplies by zero weights: it must not hold NaN bit patterns
 #pragma unroll
-    for (int g = 0; g < geo::G; ++g)
-        *reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW + 2 * R) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < geo::G; ++g)
+            *reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW + 2 * R) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        // unpadded rows: pass 1 rewrites the whole region every tile, but a warp that never runs a pass 1 (tail) must
+        // not leave NaN patterns where the bank phase reads
+        for (int i = lane; i < geo::XWARP / 4; i += 32) reinterpret_cast<float4*>(xw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int i = tid; i < n_lq * geo::SLOTS; i += kThreads) s_logq[i] = 0.f;
 
     // pass-2 role of this lane: pair g2 of the warp, column k1
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
     // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
     // of the current tile run (those need few registers), so the FFT stage never waits on HBM
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead)
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2;
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && TEAMS == 1;     // (24-warp CTAs have no registers to spare)
     InT raw[geo::G][geo::NLOAD];
     auto prefetch = [&](uint32_t tile) {
         if constexpr (kPrefetch) {
@@ -251,10 +275,12 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             }
         }
     };
-    if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
-    __syncthreads();          // mbarrier init + pads visible
+    const uint32_t tile_stride = gridDim.x * TEAMS;
+    const uint32_t tile_first = blockIdx.x * TEAMS + team;
+    if (tile_first < n_tiles) prefetch(tile_first);
+    __syncthreads();          // mbarrier init + pads visible (the only CTA-wide barrier)
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
         const uint32_t pair0 = tile * geo::PPT;
 
         // =========================== FFT stage (per warp) =======================================
@@ -280,6 +306,14 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                             for (int j = 0; j < R; ++j) raw[g][j] = __ldg(src + 32 * j);
 #pragma unroll
                             for (int j = R; j < geo::NLOAD; ++j) raw[g][j] = b_ok ? __ldg(src + 32 * j) : (InT)0;
+                            // pull the samples this warp needs in its NEXT tile into L2 (one 128-byte line per lane)
+                            const uint32_t gpn = gp + tile_stride * geo::PPT;
+                            if (gpn < n_pairs) {
+                                const uint32_t clipn = fast_div(gpn, p.ppc_magic, p.ppc_shift);
+                                const InT* nsrc = in + (int64_t)clipn * p.clip_stride + (gpn - clipn * ppc) * geo::NFFT;
+                                if (lane * 128 < (int)(geo::NLOAD * 32 * sizeof(InT)) + 128)
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(nsrc) + lane * 128));
+                            }
                         }
                         if (bit_detect) {
                             uint32_t o0 = 0, o1 = 0, o2 = 0;
@@ -324,7 +358,10 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                     fft_r<R>(x);
                     ulonglong2* row = reinterpret_cast<ulonglong2*>(xw + g * geo::XPAIR + lane * geo::XROW);
 #pragma unroll
-                    for (int k = 0; k < R; k += 2) row[k / 2] = make_ulonglong2(x[k], x[k + 1]);
+                    for (int k = 0; k < R; k += 2) {
+                        const int c = k / 2;                       // float4 column; swizzled: c ^ (row & 7)
+                        row[SWZ ? ((c & ~7) | ((c & 7) ^ (lane & 7))) : c] = make_ulonglong2(x[k], x[k + 1]);
+                    }
                 }
             }
             __syncwarp();
@@ -339,13 +376,28 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             {
                 const float* col = xw + g2 * geo::XPAIR + 2 * k1;
                 f2 z[32], c[32];
+                // twiddles W^(k1 n2): n2 < 16 come from the table, the upper half is derived with one packed complex
+                // multiply by W^(16 k1) each -- arithmetic is cheap here, shared-memory wavefronts are not
+                const f2 w16 = reinterpret_cast<const f2*>(s_tw4 + 8 * 32)[lane];
 #pragma unroll
-                for (int n2 = 0; n2 < 32; n2 += 2) {
+                for (int n2 = 0; n2 < 16; n2 += 2) {
                     const ulonglong2 t = reinterpret_cast<const ulonglong2*>(s_tw4)[(n2 / 2) * 32 + lane];
-                    z[n2] = *reinterpret_cast<const f2*>(col + n2 * geo::XROW);
-                    z[n2 + 1] = *reinterpret_cast<const f2*>(col + (n2 + 1) * geo::XROW);
                     c[n2] = t.x;
                     c[n2 + 1] = t.y;
+                    c[n2 + 16] = fma2(mul_i(t.x), bc(hi(w16)), mul2(t.x, bc(lo(w16))));
+                    c[n2 + 17] = fma2(mul_i(t.y), bc(hi(w16)), mul2(t.y, bc(lo(w16))));
+                }
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2 += 2) {
+                    if constexpr (SWZ) {
+                        const float* base = xw + g2 * geo::XPAIR + 2 * (k1 & 1);
+                        const int c = k1 >> 1;
+                        z[n2] = *reinterpret_cast<const f2*>(base + n2 * geo::XROW + 4 * ((c & ~7) | ((c & 7) ^ (n2 & 7))));
+                        z[n2 + 1] = *reinterpret_cast<const f2*>(base + (n2 + 1) * geo::XROW + 4 * ((c & ~7) | ((c & 7) ^ ((n2 + 1) & 7))));
+                    } else {
+                        z[n2] = *reinterpret_cast<const f2*>(col + n2 * geo::XROW);
+                        z[n2 + 1] = *reinterpret_cast<const f2*>(col + (n2 + 1) * geo::XROW);
+                    }
                 }
                 fft32_p2_tw(z, c, y);
             }
@@ -358,13 +410,17 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             mir[k1 == 0 ? geo::NB : geo::NB + 1] = y[0];                            // Z[N] == Z[0]; NB+1 is a dump slot
             __syncwarp();
             // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
-            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+            if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
             float* pa_row = pw + (2 * g2) * geo::PROW;
             float* pb_row = pa_row + geo::PROW;
+            f2 mv[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) mv[k2] = mir[geo::NB - (k1 + R * k2)];    // Z[N - k]
+            if constexpr (SWZ) __syncwarp();          // the power rows overwrite the mirror buffers
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
                 const int k = k1 + R * k2;
-                const f2 m = mir[geo::NB - k];                                       // Z[N - k]
+                const f2 m = mv[k2];
                 // 2A[k] = Z + conj(Zm) = (yr + mr, yi - mi);  2B[k] = (yi + mi, mr - yr)
                 const f2 u1 = add2(y[k2], m);                                        // (yr + mr, yi + mi) = (Re 2A, Re 2B)
                 const f2 u2 = add2(mul_mi(y[k2]), mul_i(m));                         // (yi - mi, mr - yr) = (Im 2A, Im 2B)
@@ -390,13 +446,13 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                 mbar_wait(s_bar, 0);
                 tables_ready = true;
             }
-            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
+            if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
         }
         if (!deps_done) {         // before this grid's first global store
             asm volatile("griddepcontrol.wait;" ::: "memory");
             deps_done = true;
         }
-        __syncthreads();
+        team_sync();
 
         // =========================== where this thread's slot goes ==============================
         int64_t out_row = -1;
@@ -430,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                 float* dst = p.out + row * p.out_cols;
                 for (int k = lane; k <= geo::NB; k += 32) dst[k] = src[k] * p.power_scale;
             }
-            __syncthreads();
+            team_sync();
             continue;
         }
 
@@ -480,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
                 }
             }
         }
-        __syncthreads();
+        team_sync();
 
         // =========================== log ========================================================
         bool silent = false;
@@ -510,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
             }
         }
         if (p.out_kind == SCF_OUT_LOG_BANK) continue;     // the next tile's first barrier orders s_part reuse
-        __syncthreads();
+        team_sync();
 
         // =========================== DCT-II, c0 := log energy ===================================
         // each thread produces two coefficients of its slot so that the log-band loads are shared
@@ -553,27 +609,48 @@ __global__ void __launch_bounds__(kThreads, SCF_MIN_CTAS) extract_kernel(const K
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int R>
-static size_t smem_bytes_r(const KParams& p)
+template <int R, int TEAMS>
+static size_t smem_bytes_rt(const KParams& p)
 {
-    using geo = Geo<R>;
+    using geo = Geo<R, (TEAMS > 1)>;
     const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
-    size_t b = (size_t)kWarps * geo::XWARP * 4 + (size_t)p.table_bytes + ((size_t)p.n_dst + n_lq) * geo::SLOTS * 4 + 16;
+    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)p.table_bytes +
+               (size_t)TEAMS * ((size_t)p.n_dst + n_lq) * geo::SLOTS * 4 + 16;
     return (b + 15) & ~(size_t)15;
+}
+
+constexpr int64_t kTeamsMinPairs = 24576;      // measured crossover: ~1600 one-second clips (tools/sweep.py)
+
+// Teams per CTA for a configuration: three 8-warp teams (24 warps per SM) for n_fft = 1024 when the tables leave
+// room for it, else one team per CTA and two CTAs per SM.  SCFEAT_TEAMS=1 forces the latter (tuning / A-B runs).
+int teams_for(int r, const KParams& p)
+{
+    static const int forced = [] { const char* e = getenv("SCFEAT_TEAMS"); return e ? atoi(e) : 0; }();
+    if (r != 32 || forced == 1) return 1;
+    if (smem_bytes_rt<32, 3>(p) > (size_t)227 * 1024) return 1;
+    // one 768-thread CTA per SM only pays off when every team gets many tiles (a small batch such as the 512-clip
+    // training batch is better balanced by 2 x 148 CTAs of one team each)
+    return (forced == 3 || p.n_pairs >= kTeamsMinPairs) ? 3 : 1;
 }
 
 size_t extract_smem_bytes(int r, const KParams& p)
 {
-    return r == 32 ? smem_bytes_r<32>(p) : r == 16 ? smem_bytes_r<16>(p) : smem_bytes_r<8>(p);
+    if (r == 32) return teams_for(r, p) == 3 ? smem_bytes_rt<32, 3>(p) : smem_bytes_rt<32, 1>(p);
+    return r == 16 ? smem_bytes_rt<16, 1>(p) : smem_bytes_rt<8, 1>(p);
+}
+
+size_t extract_smem_limit(int r, const KParams& p)
+{
+    return teams_for(r, p) == 3 ? (size_t)227 * 1024 : (size_t)(227 * 1024) / kCtasPerSm - 1024;
 }
 
 int pairs_per_tile(int r) { return kWarps * (32 / r); }
 int bank_groups(int r) { return kThreads / (2 * kWarps * (32 / r)); }
 
-template <int R, typename InT, bool FAST>
+template <int R, typename InT, bool FAST, int TEAMS>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
 {
-    auto kern = extract_kernel<R, InT, FAST>;
+    auto kern = extract_kernel<R, InT, FAST, TEAMS>;
     static size_t configured[16] = {0};          // per device: the attribute call costs microseconds per launch
     int dev = 0;
     cudaGetDevice(&dev);
@@ -582,16 +659,14 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
         if (e != cudaSuccess) return e;
         configured[dev & 15] = smem;
     }
-#ifdef SCF_GRID_CTAS
-    int64_t grid = (int64_t)num_sms * SCF_GRID_CTAS;
-#else
-    int64_t grid = (int64_t)num_sms * kCtasPerSm;
-#endif
-    if (grid > n_tiles) grid = n_tiles;
+    const int64_t ctas_per_sm = TEAMS == 1 ? kCtasPerSm : 1;
+    int64_t grid = (int64_t)num_sms * ctas_per_sm;
+    const int64_t need = (n_tiles + TEAMS - 1) / TEAMS;
+    if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreads * TEAMS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -605,25 +680,27 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
     return cudaGetLastError();
 }
 
-template <int R>
+template <int R, int TEAMS>
 static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
                             size_t smem)
 {
     if (is_f32) {
-        return fast ? launch_one<R, float, true>(p, n_tiles, num_sms, st, smem)
-                    : launch_one<R, float, false>(p, n_tiles, num_sms, st, smem);
+        return fast ? launch_one<R, float, true, TEAMS>(p, n_tiles, num_sms, st, smem)
+                    : launch_one<R, float, false, TEAMS>(p, n_tiles, num_sms, st, smem);
     }
-    return fast ? launch_one<R, int16_t, true>(p, n_tiles, num_sms, st, smem)
-                : launch_one<R, int16_t, false>(p, n_tiles, num_sms, st, smem);
+    return fast ? launch_one<R, int16_t, true, TEAMS>(p, n_tiles, num_sms, st, smem)
+                : launch_one<R, int16_t, false, TEAMS>(p, n_tiles, num_sms, st, smem);
 }
 
 cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
                            cudaStream_t st, size_t smem)
 {
     switch (r) {
-        case 32: return launch_r<32>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        case 16: return launch_r<16>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        case 8: return launch_r<8>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 32:
+            return teams_for(r, p) == 3 ? launch_r<32, 3>(is_f32, fast, p, n_tiles, num_sms, st, smem)
+                                        : launch_r<32, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 16: return launch_r<16, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 8: return launch_r<8, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
 }
