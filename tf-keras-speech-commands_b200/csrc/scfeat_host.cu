@@ -421,7 +421,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         }
     }
     auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-    const size_t sz_tw = 8 * 32 * sizeof(float4) + 32 * sizeof(float2);    // W^(k1 n2), n2 < 16, then W^(16 k1)
+    const size_t sz_tw = 4 * 32 * sizeof(float4) + 32 * sizeof(float4);    // W^(k1 n2), n2 < 8, then (W^(8 k1), W^(16 k1))
     p->off_wts = (int)sz_tw;
     p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
     p->off_tasks = (int)align16(p->off_dct + dct_t.size() * 4);
@@ -435,17 +435,18 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         {
             const int R = p->radix_r, N = cfg->n_fft;
             float4* tw = reinterpret_cast<float4*>(blob.data());
-            for (int jj = 0; jj < 8; ++jj)
+            for (int jj = 0; jj < 4; ++jj)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int k1 = lane % R;
                     const double a0 = -2.0 * M_PI * (double)((k1 * (2 * jj)) % N) / N;
                     const double a1 = -2.0 * M_PI * (double)((k1 * (2 * jj + 1)) % N) / N;
                     tw[jj * 32 + lane] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
                 }
-            float2* w16 = reinterpret_cast<float2*>(tw + 8 * 32);
+            float4* wq = tw + 4 * 32;
             for (int lane = 0; lane < 32; ++lane) {
-                const double a = -2.0 * M_PI * (double)(((lane % R) * 16) % N) / N;
-                w16[lane] = make_float2((float)cos(a), (float)sin(a));
+                const double a8 = -2.0 * M_PI * (double)(((lane % R) * 8) % N) / N;
+                const double a16 = -2.0 * M_PI * (double)(((lane % R) * 16) % N) / N;
+                wq[lane] = make_float4((float)cos(a8), (float)sin(a8), (float)cos(a16), (float)sin(a16));
             }
         }
         float* w = reinterpret_cast<float*>(blob.data() + p->off_wts);

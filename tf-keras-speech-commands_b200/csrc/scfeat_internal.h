@@ -51,7 +51,7 @@ struct KParams {
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
     float zero_energy;           // int16 input: frame energies below this mean "every sample was zero"
     // tables: one device blob, copied verbatim into shared memory by a single TMA bulk copy
-    //   [twiddles float4[16][32]] [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]
+    //   [twiddles float4[4][32] + float4[32]] [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]
     //   [tasks u32[n_tasks]] [task_begin i32[n_groups+1]] [qspec int2[n_q]]      (every section 16-byte aligned)
     const void* tables;
     int32_t table_bytes;

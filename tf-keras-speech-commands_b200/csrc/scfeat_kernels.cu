@@ -376,17 +376,19 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
             {
                 const float* col = xw + g2 * geo::XPAIR + 2 * k1;
                 f2 z[32], c[32];
-                // twiddles W^(k1 n2): n2 < 16 come from the table, the upper half is derived with one packed complex
-                // multiply by W^(16 k1) each -- arithmetic is cheap here, shared-memory wavefronts are not
-                const f2 w16 = reinterpret_cast<const f2*>(s_tw4 + 8 * 32)[lane];
+                // twiddles W^(k1 n2): n2 < 8 come from the table, the rest is derived with packed complex multiplies by
+                // W^(8 k1) and W^(16 k1) -- arithmetic is cheap here, shared-memory wavefronts are not
+                const ulonglong2 wq = reinterpret_cast<const ulonglong2*>(s_tw4 + 4 * 32)[lane];     // (W^(8 k1), W^(16 k1))
 #pragma unroll
-                for (int n2 = 0; n2 < 16; n2 += 2) {
+                for (int n2 = 0; n2 < 8; n2 += 2) {
                     const ulonglong2 t = reinterpret_cast<const ulonglong2*>(s_tw4)[(n2 / 2) * 32 + lane];
                     c[n2] = t.x;
                     c[n2 + 1] = t.y;
-                    c[n2 + 16] = fma2(mul_i(t.x), bc(hi(w16)), mul2(t.x, bc(lo(w16))));
-                    c[n2 + 17] = fma2(mul_i(t.y), bc(hi(w16)), mul2(t.y, bc(lo(w16))));
                 }
+#pragma unroll
+                for (int n2 = 0; n2 < 8; ++n2) c[n2 + 8] = fma2(mul_i(c[n2]), bc(hi(wq.x)), mul2(c[n2], bc(lo(wq.x))));
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) c[n2 + 16] = fma2(mul_i(c[n2]), bc(hi(wq.y)), mul2(c[n2], bc(lo(wq.y))));
 #pragma unroll
                 for (int n2 = 0; n2 < 32; n2 += 2) {
                     if constexpr (SWZ) {
