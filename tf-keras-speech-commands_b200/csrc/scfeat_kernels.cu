@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    const int team_floats = (p.n_dst + n_lq) * geo::SLOTS;
+    const int team_floats = (p.n_dst + n_lq + 2) * geo::SLOTS;      // partial sums, log bands, output row ids (int64)
     float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes) + team * team_floats;
     float* s_logq = s_part + p.n_dst * geo::SLOTS;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + p.table_bytes) + TEAMS * team_floats);
@@ -556,18 +556,39 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
             if (silent) v = 0.f;
             const float lv = __logf(fmaxf(v, SCF_EPS));          // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
             if (p.out_kind == SCF_OUT_LOG_BANK) {
-                if (out_row >= 0) {
-                    if (p.n_peers == 0) {
-                        p.out[out_row * p.out_cols + q] = lv;
-                    } else {
-                        for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(p.peer_row0 + out_row) * p.out_cols + q] = lv;
-                    }
+                if (p.n_peers != 0) {
+                    s_logq[slot * p.out_cols + q] = lv;         // staged for the coalesced peer stores below
+                } else if (out_row >= 0) {
+                    p.out[out_row * p.out_cols + q] = lv;
                 }
             } else {
                 s_logq[q * geo::SLOTS + slot] = lv;
             }
         }
-        if (p.out_kind == SCF_OUT_LOG_BANK) continue;     // the next tile's first barrier orders s_part reuse
+        // Fused all-gather: the finished rows of this tile sit contiguously in shared memory [slot][col]; every thread
+        // pushes consecutive floats, so each warp writes whole 128-byte segments to every peer's cache over NVLink
+        // (8-byte scattered stores per thread were 3x slower than a separate NCCL all-gather at 8 GPUs).
+        auto push_to_peers = [&](float* stage) {
+            int64_t* s_rows = reinterpret_cast<int64_t*>(s_logq + n_lq * geo::SLOTS);
+            if (grp == 0) s_rows[slot] = out_row;
+            team_sync();
+            const int n = geo::SLOTS * p.out_cols;
+            for (int i = tid; i < n; i += kThreads) {
+                const int sl = i / p.out_cols;
+                const int64_t row = s_rows[sl];
+                if (row < 0) continue;
+                const float v = stage[i];
+                const int64_t off = (p.peer_row0 + row) * p.out_cols + (i - sl * p.out_cols);
+                for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
+            }
+        };
+        if (p.out_kind == SCF_OUT_LOG_BANK) {
+            if (p.n_peers != 0) {
+                push_to_peers(s_logq);
+                team_sync();                              // s_logq is rewritten by the next tile's log phase
+            }
+            continue;                                     // the next tile's first barrier orders s_part reuse
+        }
         team_sync();
 
         // =========================== DCT-II, c0 := log energy ===================================
@@ -591,20 +612,17 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
             float va = a0 + a1;
             const float vb = b0 + b1;
             if (c == 0) va = s_logq[p.n_filt * geo::SLOTS + slot];
-            if (out_row >= 0) {
-                if (p.n_peers == 0) {
-                    float* o = p.out + out_row * p.out_cols + c;
-                    o[0] = va;
-                    if (two) o[1] = vb;
-                } else {
-                    for (int r = 0; r < p.n_peers; ++r) {
-                        float* o = p.peer_out[r] + (p.peer_row0 + out_row) * p.out_cols + c;
-                        o[0] = va;
-                        if (two) o[1] = vb;
-                    }
-                }
+            if (p.n_peers != 0) {
+                float* o = s_part + slot * p.out_cols + c;       // s_part is free during the DCT phase: stage the rows
+                o[0] = va;
+                if (two) o[1] = vb;
+            } else if (out_row >= 0) {
+                float* o = p.out + out_row * p.out_cols + c;
+                o[0] = va;
+                if (two) o[1] = vb;
             }
         }
+        if (p.n_peers != 0) push_to_peers(s_part);
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no
         // thread reads after the bank stage; s_part / s_logq are rewritten only behind later barriers.
     }
@@ -617,7 +635,7 @@ static size_t smem_bytes_rt(const KParams& p)
     using geo = Geo<R, (TEAMS > 1)>;
     const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
     size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)p.table_bytes +
-               (size_t)TEAMS * ((size_t)p.n_dst + n_lq) * geo::SLOTS * 4 + 16;
+               (size_t)TEAMS * ((size_t)p.n_dst + n_lq + 2) * geo::SLOTS * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
