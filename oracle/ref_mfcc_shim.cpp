@@ -28,6 +28,19 @@ int ref_mfcc(const float* audio, int n, int sample_rate, int window, int hop, in
     return (int)feats.size();
 }
 
+// Same with the central-difference deltas of mfcc.h:432-441 appended: out holds frames * 2 * n_coeffs floats.
+int ref_mfcc_delta(const float* audio, int n, int sample_rate, int window, int hop, int n_fft, int n_coeffs, int n_filt,
+                   int low_freq, int high_freq, float* out)
+{
+    if (n < window) return 0;
+    std::vector<float> buf(audio, audio + n);
+    std::vector<std::vector<float>> feats;
+    mfcc::mfcc<float>(feats, buf, sample_rate, window, hop, n_fft, n_coeffs, n_filt, low_freq, high_freq, false, true, false);
+    for (size_t i = 0; i < feats.size(); ++i)
+        for (int j = 0; j < 2 * n_coeffs; ++j) out[i * 2 * n_coeffs + j] = feats[i][j];
+    return (int)feats.size();
+}
+
 // The triangular bank alone (mfcc.h:230-264), row-major [n_filt][n_fft/2+1] doubles.
 void ref_filterbanks(int sample_rate, int n_fft, int n_filt, int low_freq, int high_freq,
                      double* out)

@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 
 
+@pytest.fixture(scope='session', autouse=True)
+def built_library():
+    """libscfeat.so is a build artefact (git-ignored): compile it with nvcc when a fresh checkout runs the tests
+    (nvcc cross-compiles sm_100a without a GPU).  On the GPU box the prebuilt file travels with the snapshot."""
+    import scfeat
+    if not os.path.exists(scfeat._lib.LIB_PATH):
+        scfeat.build()
+    return scfeat._lib.LIB_PATH
+
+
 @pytest.fixture(scope='session')
 def example_pcm():
     z = np.load(os.path.join(GOLDEN, 'example_pcm.npz'))

@@ -100,6 +100,12 @@ def main():
     cpp['mfcc_params_json_synth'] = np.stack([cpp_mfcc(lib, a, 16000, 1024, 512, 1024, 20, 20) for a in synth_f])
     cpp['mfcc_512_256_512_20_13'] = np.stack([cpp_mfcc(lib, a, 16000, 512, 256, 512, 13, 20) for a in audio[:2]])
     cpp['mfcc_preproc'] = np.stack([cpp_mfcc(lib, a, 16000, 1024, 512, 1024, 20, 20, pre=1) for a in audio[:2]])
+    lib.ref_mfcc_delta.restype = ctypes.c_int
+    lib.ref_mfcc_delta.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 8 + [ctypes.c_void_p]
+    a0 = np.ascontiguousarray(audio[0], dtype=np.float32)
+    dl = np.zeros((30, 40), dtype=np.float32)
+    assert lib.ref_mfcc_delta(a0.ctypes.data, len(a0), 16000, 1024, 512, 1024, 20, 20, 0, 16000, dl.ctypes.data) == 30
+    cpp['mfcc_central_delta'] = dl
     bank = np.zeros((20, 513))
     lib.ref_filterbanks(16000, 1024, 20, 0, 16000, bank.ctypes.data)
     cpp['bank_16000_20_1024'] = bank
@@ -124,3 +130,48 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def load_reference_postprocess():
+    """ThresholdDecoder / TriggerDetector taken verbatim from /root/reference/listen.py by AST extraction (the module
+    itself imports pyaudio / tensorflow / MNN and cannot be imported here)."""
+    import ast
+    import math
+    src = open(os.path.join(REF, 'listen.py')).read()
+    tree = ast.parse(src)
+    ns = {'np': np, 'math': math}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ('ThresholdDecoder', 'TriggerDetector'):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), 'listen.py', 'exec'), ns)
+    return ns['ThresholdDecoder'], ns['TriggerDetector']
+
+
+def make_postprocess_golden():
+    TD, TR = load_reference_postprocess()
+    rng = np.random.default_rng(21)
+    out = {}
+    raws = np.concatenate([[0.0, 1.0, 1e-12, 1 - 1e-12, 0.5, 0.2, 0.8], rng.random(400), rng.random(100) ** 8,
+                           1 - rng.random(100) ** 8])
+    out['raw'] = raws
+    for name, cfg, center in (('default', ((6, 4),), 0.2), ('two', ((6, 4), (-2, 3)), 0.5), ('narrow', ((0, 0.1),), 0.5)):
+        d = TD(cfg, center)
+        out['decode_' + name] = np.array([d.decode(float(r)) for r in raws])
+        out['encode_' + name] = np.array([d.encode(float(t)) for t in np.linspace(0.01, 0.99, 50)])
+    classes = ['background', 'up', 'down', 'left']
+    T = 600
+    idx = rng.integers(0, 4, size=T)
+    idx[100:160] = 2
+    idx[300:420] = 1
+    score = rng.random(T)
+    score[100:160] = 0.9
+    score[300:420] = 0.95
+    for chunk in (1024, 1600, 4096):
+        det = TR(chunk, classes, 0.5, 3)
+        out['trigger_%d' % chunk] = np.array([det.update(int(i), float(s)) for i, s in zip(idx, score)])
+    out['trigger_idx'], out['trigger_score'] = idx, score
+    np.savez_compressed(os.path.join(HERE, 'ref_postprocess.npz'), **out)
+    print('ref_postprocess.npz', os.path.getsize(os.path.join(HERE, 'ref_postprocess.npz')) // 1024, 'KiB')
+
+
+if __name__ == '__main__' and os.environ.get('SCF_GOLDEN_POSTPROCESS', '1') == '1':
+    make_postprocess_golden()

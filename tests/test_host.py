@@ -169,3 +169,17 @@ def test_dlpack_capsule_plumbing_on_cpu():
     del cap2
     gc.collect()
     assert len(deleted) == 2            # nobody consumed it: the capsule destructor released it
+
+
+def test_add_deltas_both_definitions(ref_cpp):
+    """kind='diff' is the Python path's first difference; kind='central' reproduces the C++ twin's deltas
+    (mfcc.h:432-441) on the twin's own MFCC output."""
+    both = ref_cpp['mfcc_central_delta']
+    base = both[:, :20]
+    got = scfeat.data_utils.add_deltas(base, kind='central')
+    np.testing.assert_allclose(got, both, rtol=0, atol=1e-6)
+    d = scfeat.data_utils.add_deltas(base)
+    assert d.shape == (30, 40) and not d[0, 20:].any()
+    np.testing.assert_array_equal(d[1:, 20:], base[1:] - base[:-1])
+    with pytest.raises(ValueError):
+        scfeat.data_utils.add_deltas(base, kind='other')

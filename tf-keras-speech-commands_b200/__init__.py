@@ -7,7 +7,7 @@ The directory name contains '-', so import it with importlib (or via the top-lev
     import scfeat
     feats = scfeat.data_utils.extract_features_batch(pcm_int16)
 """
-from . import _lib, bark_feature, cache, data_utils, dist, listener, params, plan, sonopy  # noqa: F401
+from . import _lib, bark_feature, cache, data_utils, dist, listener, params, plan, postprocess, sonopy  # noqa: F401
 from ._lib import ScfError, build  # noqa: F401
 from .plan import Plan, get_plan, launch_count, measure_fp32_flops  # noqa: F401
 

@@ -18,12 +18,14 @@ __device__ __forceinline__ float lo(f2 v)
 {
     float a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    (void)b;
     return a;
 }
 __device__ __forceinline__ float hi(f2 v)
 {
     float a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    (void)a;
     return b;
 }
 __device__ __forceinline__ f2 add2(f2 a, f2 b)

@@ -255,7 +255,12 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
     // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
     // of the current tile run (those need few registers), so the FFT stage never waits on HBM
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead)
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && TEAMS == 1;     // (24-warp CTAs have no registers to spare)
+#ifdef SCF_NO_REG_PREFETCH
+    constexpr bool kPrefetch = false;
+#else
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && TEAMS == 1;
+#endif
+        // (24-warp CTAs have no registers to spare)
     InT raw[geo::G][geo::NLOAD];
     auto prefetch = [&](uint32_t tile) {
         if constexpr (kPrefetch) {

@@ -33,10 +33,22 @@ def audio_to_buffer(audio):
     return (np.asarray(audio) * (np.iinfo(np.int16).max + 1)).astype('<i2').tobytes()
 
 
-def add_deltas(features):
-    """appends the first difference between adjacent timesteps (row 0 -> zeros)"""
+def add_deltas(features, kind='diff'):
+    """appends delta features on the last axis.
+    kind='diff'    : the Python path (common/data_utils.py:50-58): first difference, row 0 -> zeros;
+    kind='central' : the C++ twin (inference/tflite/mfcc.h:432-441): (f[i+1] - f[i-1]) / 2 with the edges clamped."""
+    features = np.asarray(features)
     deltas = np.zeros_like(features)
-    deltas[1:] = features[1:] - features[:-1]
+    if kind == 'diff':
+        deltas[1:] = features[1:] - features[:-1]
+    elif kind == 'central':
+        n = len(features)
+        if n:
+            nxt = np.minimum(np.arange(n) + 1, n - 1)
+            prv = np.maximum(np.arange(n) - 1, 0)
+            deltas = (features[nxt] - features[prv]) / 2
+    else:
+        raise ValueError("kind must be 'diff' or 'central'")
     return np.concatenate([features, deltas], -1)
 
 
