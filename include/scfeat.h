@@ -134,6 +134,14 @@ int scf_extract_host_i16(const scf_plan* plan, const int16_t* h_pcm, int64_t n_c
 int scf_extract_host_f32(const scf_plan* plan, const float* h_audio, int64_t n_clips, int64_t clip_stride,
                          int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out);
 
+/* Asynchronous form of scf_extract_host_i16 for producers that keep feeding batches: returns as soon as the copies
+ * and the kernel are enqueued.  Two internal staging slots alternate, so the H2D copy of call i+1 overlaps the
+ * kernel and the D2H copy of call i.  h_pcm / h_out must stay valid (and should be pinned) until scf_host_sync()
+ * returns; results of all earlier async calls are complete after scf_host_sync(). */
+int scf_extract_host_i16_async(const scf_plan* plan, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
+                               int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out);
+int scf_host_sync(const scf_plan* plan);
+
 /* Library-owned output handed over as a DLPack capsule payload: *dl_out is a DLManagedTensor*
  * (kDLCUDA, float32, shape [n_clips, frames_per_clip, out_cols]) whose deleter frees the device
  * buffer; consumable by tf.experimental.dlpack.from_dlpack / torch.from_dlpack. */

@@ -327,6 +327,28 @@ def test_device_api_and_dlpack(example_pcm):
     assert np.array_equal(d_out.cpu().numpy(), host)
 
 
+def test_async_host_api_matches_sync(example_pcm):
+    import torch
+    _, pcm = example_pcm
+    plan = scfeat.get_plan()
+    rng = np.random.default_rng(9)
+    batches = [rng.integers(-32768, 32768, size=(64, 16000), dtype=np.int16) for _ in range(5)]
+    batches[2][:8] = pcm
+    pinned_in = [torch.from_numpy(b).pin_memory().numpy() for b in batches]
+    outs = [torch.empty((64, 30, 20), dtype=torch.float32).pin_memory().numpy() for _ in batches]
+    for b, o in zip(pinned_in, outs):
+        plan.extract_host_async(b, o)
+    plan.host_sync()
+    for b, o in zip(batches, outs):
+        assert np.array_equal(o, plan.extract_host(b))
+    lengths = np.full(64, 9000, dtype=np.int32)
+    plan.extract_host_async(pinned_in[0], outs[0], lengths=lengths)
+    plan.host_sync()
+    assert np.array_equal(outs[0], plan.extract_host(batches[0], lengths=lengths))
+    with pytest.raises(ValueError):
+        plan.extract_host_async(batches[0].astype(np.float32), outs[0])
+
+
 # ------------------------------------------------------------------ config 4: streaming
 @pytest.mark.parametrize('chunk', [1600, 1024, 512, 3000])
 def test_stream_matches_listener_oracle(example_pcm, chunk):

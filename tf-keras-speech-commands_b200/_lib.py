@@ -27,6 +27,7 @@ EXPORTS = [
     'scf_config_default', 'scf_num_frames', 'scf_out_cols', 'scf_build_bank', 'scf_build_dct',
     'scf_plan_create', 'scf_plan_destroy', 'scf_plan_config',
     'scf_extract_i16', 'scf_extract_f32', 'scf_extract_host_i16', 'scf_extract_host_f32',
+    'scf_extract_host_i16_async', 'scf_host_sync',
     'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_allgather_nccl',
     'scf_stream_create', 'scf_stream_destroy', 'scf_stream_reset', 'scf_stream_push_i16',
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
@@ -98,6 +99,8 @@ def lib():
         host_args = [vp, vp, i64, i64, i32, vp, i32, f32p]
         L.scf_extract_host_i16.argtypes = host_args
         L.scf_extract_host_f32.argtypes = host_args
+        L.scf_extract_host_i16_async.argtypes = host_args
+        L.scf_host_sync.argtypes = [vp]
         L.scf_extract_i16_dlpack.argtypes = [vp, vp, i64, i64, i32, vp, i32, ctypes.POINTER(vp), vp]
         L.scf_extract_i16_gather.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(vp), i32, i32, i64, vp]
         L.scf_allgather_nccl.argtypes = [vp, vp, i64, vp, vp]

@@ -167,6 +167,17 @@ struct Workspace {          // scratch for the host-buffer entry points
     cudaStream_t st = nullptr;
     cudaStream_t st2 = nullptr;
     cudaEvent_t ev = nullptr;
+    // scf_extract_host_i16_async: two alternating slots, each with its own stream and staging buffers
+    struct Slot {
+        void* d_in = nullptr;
+        size_t in_bytes = 0;
+        float* d_out = nullptr;
+        size_t out_bytes = 0;
+        int32_t* d_len = nullptr;
+        size_t len_bytes = 0;
+        cudaStream_t st = nullptr;
+    } slot[2];
+    unsigned next_slot = 0;
 };
 
 }  // namespace scf
@@ -346,6 +357,12 @@ static void free_plan_tables(scf_plan* p)
     if (p->ws.st) cudaStreamDestroy(p->ws.st);
     if (p->ws.st2) cudaStreamDestroy(p->ws.st2);
     if (p->ws.ev) cudaEventDestroy(p->ws.ev);
+    for (auto& sl : p->ws.slot) {
+        if (sl.d_in) cudaFree(sl.d_in);
+        if (sl.d_out) cudaFree(sl.d_out);
+        if (sl.d_len) cudaFree(sl.d_len);
+        if (sl.st) cudaStreamDestroy(sl.st);
+    }
 }
 
 static int plan_create(const scf_config* cfg, scf_plan** out)
@@ -636,6 +653,54 @@ static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int
     return SCF_OK;
 }
 
+static int extract_host_async(const scf_plan* plan, const int16_t* h_in, int64_t n_clips, int64_t clip_stride,
+                              int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+{
+    if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
+    if (n_clips < 0 || clip_len < 0) return fail(SCF_ERR_INVALID, "negative size");
+    if (n_clips == 0) return SCF_OK;
+    if (!h_in || clip_stride < clip_len) return fail(SCF_ERR_INVALID, "bad input pointer / stride");
+    const int64_t fpc = scf_num_frames(clip_len, plan->cfg.window, plan->cfg.hop);
+    if (fpc == 0) return SCF_OK;
+    if (!h_out) return fail(SCF_ERR_INVALID, "output pointer is NULL");
+    DeviceGuard guard(plan->device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    Workspace& ws = const_cast<scf_plan*>(plan)->ws;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    Workspace::Slot& sl = ws.slot[ws.next_slot++ & 1];
+    if (!sl.st) SCF_CUDA(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+    const size_t in_bytes = (size_t)((n_clips - 1) * clip_stride + clip_len) * 2;
+    const size_t out_bytes = (size_t)n_clips * fpc * plan->out_cols * sizeof(float);
+    if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes || (h_lengths && (size_t)n_clips * 4 > sl.len_bytes))
+        SCF_CUDA(cudaStreamSynchronize(sl.st));       // the slot's buffers are about to be reallocated
+    int rc;
+    if ((rc = grow(&sl.d_in, &sl.in_bytes, in_bytes)) || (rc = grow(&sl.d_out, &sl.out_bytes, out_bytes))) return rc;
+    const int32_t* d_len = nullptr;
+    if (h_lengths) {
+        if ((rc = grow(&sl.d_len, &sl.len_bytes, (size_t)n_clips * 4))) return rc;
+        SCF_CUDA(cudaMemcpyAsync(sl.d_len, h_lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, sl.st));
+        d_len = sl.d_len;
+    }
+    // stream order on the slot's stream also protects its staging buffers from the call two steps later
+    SCF_CUDA(cudaMemcpyAsync(sl.d_in, h_in, in_bytes, cudaMemcpyHostToDevice, sl.st));
+    if (pad == SCF_PAD_NONE && h_lengths) SCF_CUDA(cudaMemsetAsync(sl.d_out, 0, out_bytes, sl.st));
+    rc = extract_device(plan, false, sl.d_in, n_clips, clip_stride, clip_len, d_len, pad, sl.d_out, nullptr, 0, 0, sl.st);
+    if (rc) return rc;
+    SCF_CUDA(cudaMemcpyAsync(h_out, sl.d_out, out_bytes, cudaMemcpyDeviceToHost, sl.st));
+    return SCF_OK;
+}
+
+static int host_sync(const scf_plan* plan)
+{
+    if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
+    DeviceGuard guard(plan->device);
+    Workspace& ws = const_cast<scf_plan*>(plan)->ws;
+    std::lock_guard<std::mutex> lock(ws.mu);
+    for (auto& sl : ws.slot)
+        if (sl.st) SCF_CUDA(cudaStreamSynchronize(sl.st));
+    return SCF_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // DLPack hand-off
 // ---------------------------------------------------------------------------------------------
@@ -767,6 +832,14 @@ int scf_extract_host_f32(const scf_plan* plan, const float* h_audio, int64_t n_c
 {
     return extract_host(plan, true, h_audio, n_clips, clip_stride, clip_len, h_lengths, pad, h_out);
 }
+
+int scf_extract_host_i16_async(const scf_plan* plan, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
+                               int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+{
+    return extract_host_async(plan, h_pcm, n_clips, clip_stride, clip_len, h_lengths, pad, h_out);
+}
+
+int scf_host_sync(const scf_plan* plan) { return host_sync(plan); }
 
 int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride,
                            int32_t clip_len, const int32_t* d_lengths, int32_t pad, void** dl_out, void* cuda_stream)

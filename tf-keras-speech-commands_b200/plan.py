@@ -74,6 +74,29 @@ class Plan:
             check(fn(self._h, a.ctypes.data, n, L, L, lp, pad, out.ctypes.data))
         return out[0] if single else out
 
+    def extract_host_async(self, clips, out, lengths=None, pad=PAD_FRONT_ZERO):
+        """Enqueue one batch (int16 [n, L], C-contiguous, ideally pinned) and return immediately; `out` (float32
+        [n, frames(L), cols], C-contiguous, ideally pinned) is valid after host_sync().  Two staging slots alternate
+        inside the library, so the upload of the next batch overlaps the kernel and download of this one.  The
+        caller keeps `clips`, `lengths` and `out` alive until host_sync()."""
+        a = np.asarray(clips)
+        if a.ndim != 2 or a.dtype != np.int16 or not a.flags['C_CONTIGUOUS']:
+            raise ValueError('clips must be a C-contiguous int16 [n, L] array')
+        n, L = a.shape
+        shape = (n, self.frames(L), self.out_cols)
+        if out.shape != shape or out.dtype != np.float32 or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a C-contiguous float32 array of shape %r' % (shape,))
+        lp = None
+        if lengths is not None:
+            if lengths.dtype != np.int32 or lengths.shape != (n,) or not lengths.flags['C_CONTIGUOUS']:
+                raise ValueError('lengths must be a C-contiguous int32 [n] array (kept alive by the caller)')
+            lp = lengths.ctypes.data
+        check(_lib.lib().scf_extract_host_i16_async(self._h, a.ctypes.data, n, L, L, lp, pad, out.ctypes.data))
+
+    def host_sync(self):
+        """Wait for every extract_host_async() issued on this plan."""
+        check(_lib.lib().scf_host_sync(self._h))
+
     # ---- raw device pointers (torch / cupy / DLPack producers hand in .data_ptr()) -------------
     def extract_device(self, d_in, n_clips, clip_len, d_out, clip_stride=None, d_lengths=None, pad=PAD_FRONT_ZERO,
                        stream=0, is_f32=False):
