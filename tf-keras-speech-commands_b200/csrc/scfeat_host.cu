@@ -421,11 +421,10 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         std::vector<double> bank;
         build_bank(cfg, bank);
         const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
-        // the frame energy is always computed: the cepstrum needs it as c0, and the fast int16 path derives its
-        // "frame is all zero" decision from it (scfeat_kernels.cu)
-        build_tasks(bank, cfg->n_filt, p->n_bins, true, bank_groups(p->radix_r), tl);
+        // (the frame energy -- c0 of the cepstrum -- is summed in the FFT stage, not as a bank row)
+        build_tasks(bank, cfg->n_filt, p->n_bins, false, bank_groups(p->radix_r), tl);
         p->n_tasks = (int)tl.words.size();
-        p->n_q = (int)tl.qspec.size();
+        p->n_q = cfg->n_filt + (cep ? 1 : 0);
         p->n_dst = tl.n_dst;
         p->n_filt4 = (cfg->n_filt + 3) & ~3;
         if (cep) {

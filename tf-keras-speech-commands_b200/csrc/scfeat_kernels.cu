@@ -189,9 +189,10 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    const int team_floats = (p.n_dst + n_lq + 2) * geo::SLOTS;      // partial sums, log bands, output row ids (int64)
+    const int team_floats = (p.n_dst + n_lq + 3) * geo::SLOTS;      // partial sums, log bands, row ids (int64), frame energies
     float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes) + team * team_floats;
     float* s_logq = s_part + p.n_dst * geo::SLOTS;
+    float* s_energy = s_logq + (n_lq + 2) * geo::SLOTS;              // [slot] frame energy, written by the FFT stage
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + p.table_bytes) + TEAMS * team_floats);
     float* xw = s_xch + warp * geo::XWARP;
     auto team_sync = [&]() {
@@ -421,6 +422,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
             float* pa_row = pw + (2 * g2) * geo::PROW;
             float* pb_row = pa_row + geo::PROW;
             f2 mv[16];
+            f2 esum = pk(0.f, 0.f);
 #pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) mv[k2] = mir[geo::NB - (k1 + R * k2)];    // Z[N - k]
             if constexpr (SWZ) __syncwarp();          // the power rows overwrite the mirror buffers
@@ -434,11 +436,23 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
                 const f2 pp = fma2(u2, u2, mul2(u1, u1));                            // (|2A|^2, |2B|^2)
                 pa_row[k] = lo(pp);
                 pb_row[k] = hi(pp);
+                esum = add2(esum, pp);
             }
             if (k1 == 0) {                                                           // bin n_fft/2 mirrors onto itself
                 const f2 pp = mul2(mul2(y[16], y[16]), bc(4.f));
                 pa_row[geo::NB] = lo(pp);
                 pb_row[geo::NB] = hi(pp);
+                esum = add2(esum, pp);
+            }
+            // frame energies (sum of the power row; c0 of the cepstrum, bark_feature.py:173): the values are in
+            // registers right now, so a warp reduction is cheaper than a 513-tap pseudo-filter in the bank phase
+#pragma unroll
+            for (int m = R / 2; m >= 1; m >>= 1) esum = add2(esum, __shfl_xor_sync(0xffffffffu, esum, m));
+            if (k1 == 0) {
+                const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
+                float* e = s_energy + 2 * (warp * geo::G + g2);
+                e[0] = za ? 0.f : lo(esum) * p.power_scale;
+                e[1] = zb ? 0.f : hi(esum) * p.power_scale;
             }
             if (__builtin_expect(zero_mask != 0, 0)) {                     // rare: exact zeros for silent frames
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
@@ -546,18 +560,18 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
         team_sync();
 
         // =========================== log ========================================================
+        const float frame_energy = s_energy[slot];
         bool silent = false;
-        if constexpr (kEnergyZero) {
-            const int2 qe = s_qspec[p.n_filt];                 // the frame-energy quantity is always the last one
-            float e = s_part[qe.x * geo::SLOTS + slot];
-            for (int j = 1; j < qe.y; ++j) e += s_part[(qe.x + j) * geo::SLOTS + slot];
-            silent = e < p.zero_energy;
-        }
-        const int n_q_out = (p.out_kind == SCF_OUT_LOG_BANK) ? p.n_filt : p.n_q;
-        for (int q = grp; q < n_q_out; q += geo::NGRP) {
-            const int2 qs = s_qspec[q];
-            float v = s_part[qs.x * geo::SLOTS + slot];
-            for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
+        if constexpr (kEnergyZero) silent = frame_energy < p.zero_energy;
+        for (int q = grp; q < p.n_q; q += geo::NGRP) {            // n_q = n_filt (+1: the energy, cepstrum only)
+            float v;
+            if (q < p.n_filt) {
+                const int2 qs = s_qspec[q];
+                v = s_part[qs.x * geo::SLOTS + slot];
+                for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
+            } else {
+                v = frame_energy;
+            }
             if (silent) v = 0.f;
             const float lv = __logf(fmaxf(v, SCF_EPS));          // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
             if (p.out_kind == SCF_OUT_LOG_BANK) {
@@ -640,7 +654,7 @@ static size_t smem_bytes_rt(const KParams& p)
     using geo = Geo<R, (TEAMS > 1)>;
     const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
     size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)p.table_bytes +
-               (size_t)TEAMS * ((size_t)p.n_dst + n_lq + 2) * geo::SLOTS * 4 + 16;
+               (size_t)TEAMS * ((size_t)p.n_dst + n_lq + 3) * geo::SLOTS * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
