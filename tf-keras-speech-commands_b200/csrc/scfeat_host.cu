@@ -194,7 +194,7 @@ struct scf_plan {
     float* d_win = nullptr;
     unsigned char* d_tab_i16 = nullptr;   // bank weights pre-multiplied by the int16 power scale
     unsigned char* d_tab_f32 = nullptr;   // ... by the float-input power scale
-    int table_bytes = 0, off_wts = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
+    int table_bytes = 0, table_small_bytes = 0, off_wts = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
     int n_tasks = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
     scf::Workspace ws;
 };
@@ -438,12 +438,15 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     }
     auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t sz_tw = 4 * 32 * sizeof(float4) + 32 * sizeof(float4);    // W^(k1 n2), n2 < 8, then (W^(8 k1), W^(16 k1))
-    p->off_wts = (int)sz_tw;
-    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
-    p->off_tasks = (int)align16(p->off_dct + dct_t.size() * 4);
+    // order: the small tables first (always staged in shared memory), then the bank weights and the DCT matrix
+    // (staged too by the classic kernel; read through L1 by the dense variants, which need the space for warps)
+    p->off_tasks = (int)sz_tw;
     p->off_tbeg = (int)align16(p->off_tasks + (size_t)p->n_tasks * 4);
     p->off_qspec = (int)align16(p->off_tbeg + tl.begin.size() * 4);
-    p->table_bytes = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
+    p->table_small_bytes = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
+    p->off_wts = p->table_small_bytes;
+    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
+    p->table_bytes = (int)align16(p->off_dct + dct_t.size() * 4);
     for (int variant = 0; variant < 2; ++variant) {
         const double ps = variant == 0 ? ps_i16 : ps_f32;
         std::vector<unsigned char> blob(p->table_bytes, 0);
@@ -514,6 +517,7 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     }
     kp.tables = is_f32 ? plan->d_tab_f32 : plan->d_tab_i16;
     kp.table_bytes = plan->table_bytes;
+    kp.table_small_bytes = plan->table_small_bytes;
     kp.off_wts = plan->off_wts;
     kp.off_dct = plan->off_dct;
     kp.off_tasks = plan->off_tasks;

@@ -51,10 +51,11 @@ struct KParams {
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
     float zero_energy;           // int16 input: frame energies below this mean "every sample was zero"
     // tables: one device blob, copied verbatim into shared memory by a single TMA bulk copy
-    //   [twiddles float4[4][32] + float4[32]] [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]
-    //   [tasks u32[n_tasks]] [task_begin i32[n_groups+1]] [qspec int2[n_q]]      (every section 16-byte aligned)
+    //   [twiddles float4[4][32] + float4[32]] [tasks u32[n_tasks]] [task_begin i32[n_groups+1]] [qspec int2[n_filt]]
+    //   [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]                 (every section 16-byte aligned)
     const void* tables;
-    int32_t table_bytes;
+    int32_t table_bytes;         // whole blob
+    int32_t table_small_bytes;   // leading part without bank weights / DCT (what the dense kernels stage)
     int32_t off_wts, off_dct, off_tasks, off_tbeg, off_qspec;
     int32_t n_tasks;
     int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)

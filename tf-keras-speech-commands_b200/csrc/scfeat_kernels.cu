@@ -58,6 +58,19 @@ struct Geo {
 
 __device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
 __device__ __forceinline__ float to_f32(float v) { return v; }
+// streaming sample loads that do not allocate in L1 (the dense kernels keep L1 for the bank weights / DCT matrix)
+__device__ __forceinline__ int16_t ld_stream(const int16_t* p)
+{
+    short v;
+    asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 // bits that are set iff the sample is not zero (-0.0f counts as zero)
 __device__ __forceinline__ uint32_t nz_bits(int16_t v) { return (uint32_t)(uint16_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
@@ -162,15 +175,20 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
     return (t + ((n - t) >> 1)) >> shift;
 }
 
-// TEAMS = 1: a CTA is one team of 8 warps (256 threads); two CTAs per SM (128 registers per thread).
-// TEAMS = 3: a CTA is three independent teams of 8 warps that share ONE copy of the tables and synchronise through
-//            their own named barriers: 24 warps per SM at 80 registers per thread (the packed FFT fits), which is
-//            what hides the FFMA2 / LDS latencies.  Needs the swizzled 8 KB-per-warp layout.
-template <int R, typename InT, bool FAST, int TEAMS>
-__global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1)
+// TEAMS = 1, DENSE = false ("classic"): a CTA is one team of 8 warps; 2 CTAs per SM, 128 registers per thread, padded
+//            exchange rows, every table in shared memory, next tile's samples prefetched into registers.
+// DENSE = true: 80 registers per thread (the packed FFT fits), XOR-swizzled 8 KB exchange region per warp, bank
+//            weights and DCT matrix read through L1 instead of shared memory -> 24 warps per SM, which is what hides the
+//            FFMA2 / LDS latencies:
+//   TEAMS = 1: 3 CTAs of one team per SM -- small jobs (CTAs of the next launch backfill through PDL);
+//   TEAMS = 3: one 768-thread CTA of three independent teams that share one table copy and synchronise through their
+//              own named barriers -- large jobs.
+template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
+__global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 : SCF_MIN_CTAS))
     extract_kernel(const KParams p, const uint32_t n_tiles)
 {
-    constexpr bool SWZ = TEAMS > 1;
+    static_assert(TEAMS == 1 || DENSE, "multi-team CTAs need the dense layout");
+    constexpr bool SWZ = DENSE;
     using geo = Geo<R, SWZ>;
     extern __shared__ __align__(16) float smem[];
 
@@ -182,18 +200,22 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
     // ---- shared memory carve-up (must match extract_smem_bytes; the table part mirrors the plan's blob) ----
     float* s_xch = smem + team * (kWarps * geo::XWARP);
     unsigned char* s_tab = reinterpret_cast<unsigned char*>(smem + TEAMS * kWarps * geo::XWARP);
+    // what is staged in shared memory: everything, except that the 3-CTAs-per-SM variant leaves the DCT matrix in
+    // global memory (read through L1 in the short DCT phase) -- that is what makes its 75 KB budget
+    constexpr bool kDctInL1 = DENSE && TEAMS == 1;
+    const int staged_bytes = kDctInL1 ? p.off_dct : p.table_bytes;
     const float4* s_tw4 = reinterpret_cast<const float4*>(s_tab);
     const float4* s_wts4 = reinterpret_cast<const float4*>(s_tab + p.off_wts);
-    const float* s_dct = reinterpret_cast<const float*>(s_tab + p.off_dct);
+    const float* s_dct = reinterpret_cast<const float*>((kDctInL1 ? static_cast<const unsigned char*>(p.tables) : s_tab) + p.off_dct);
     const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
     const int team_floats = (p.n_dst + n_lq + 3) * geo::SLOTS;      // partial sums, log bands, row ids (int64), frame energies
-    float* s_part = reinterpret_cast<float*>(s_tab + p.table_bytes) + team * team_floats;
+    float* s_part = reinterpret_cast<float*>(s_tab + staged_bytes) + team * team_floats;
     float* s_logq = s_part + p.n_dst * geo::SLOTS;
     float* s_energy = s_logq + (n_lq + 2) * geo::SLOTS;              // [slot] frame energy, written by the FFT stage
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + p.table_bytes) + TEAMS * team_floats);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + staged_bytes) + TEAMS * team_floats);
     float* xw = s_xch + warp * geo::XWARP;
     auto team_sync = [&]() {
         if constexpr (TEAMS == 1) __syncthreads();
@@ -211,7 +233,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
     // tables: ONE TMA bulk copy, waited for just before the first pass 2 (overlaps the first loads + pass 1)
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
-        bulk_g2s(s_tab, p.tables, (uint32_t)p.table_bytes, s_bar);
+        bulk_g2s(s_tab, p.tables, (uint32_t)staged_bytes, s_bar);
     }
     if constexpr (!SWZ) {
         // the 16-byte pad of every exchange row is never written by pass 1 but aliases power-row words that the
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
 #ifdef SCF_NO_REG_PREFETCH
     constexpr bool kPrefetch = false;
 #else
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && TEAMS == 1;
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;
 #endif
         // (24-warp CTAs have no registers to spare)
     InT raw[geo::G][geo::NLOAD];
@@ -309,9 +331,10 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
                             const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
                             const bool b_ok = (int)(2 * q + 1) < p.frames_per_clip;
 #pragma unroll
-                            for (int j = 0; j < R; ++j) raw[g][j] = __ldg(src + 32 * j);
+                            for (int j = 0; j < R; ++j) raw[g][j] = kDctInL1 ? ld_stream(src + 32 * j) : __ldg(src + 32 * j);
 #pragma unroll
-                            for (int j = R; j < geo::NLOAD; ++j) raw[g][j] = b_ok ? __ldg(src + 32 * j) : (InT)0;
+                            for (int j = R; j < geo::NLOAD; ++j)
+                                raw[g][j] = b_ok ? (kDctInL1 ? ld_stream(src + 32 * j) : __ldg(src + 32 * j)) : (InT)0;
                             // pull the samples this warp needs in its NEXT tile into L2 (one 128-byte line per lane)
                             const uint32_t gpn = gp + tile_stride * geo::PPT;
                             if (gpn < n_pairs) {
@@ -621,8 +644,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
                 // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
                 const float l0 = s_logq[(m + 0) * geo::SLOTS + slot], l1 = s_logq[(m + 1) * geo::SLOTS + slot];
                 const float l2 = s_logq[(m + 2) * geo::SLOTS + slot], l3 = s_logq[(m + 3) * geo::SLOTS + slot];
-                const float4 da = d4a[m >> 2];
-                const float4 db = d4b[m >> 2];
+                const float4 da = kDctInL1 ? __ldg(d4a + (m >> 2)) : d4a[m >> 2];
+                const float4 db = kDctInL1 ? __ldg(d4b + (m >> 2)) : d4b[m >> 2];
                 a0 = __fmaf_rn(l0, da.x, a0); a1 = __fmaf_rn(l1, da.y, a1);
                 a0 = __fmaf_rn(l2, da.z, a0); a1 = __fmaf_rn(l3, da.w, a1);
                 b0 = __fmaf_rn(l0, db.x, b0); b1 = __fmaf_rn(l1, db.y, b1);
@@ -648,57 +671,66 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 1 ? SCF_MIN_CTAS : 1
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int R, int TEAMS>
+template <int R, int TEAMS, bool DENSE>
 static size_t smem_bytes_rt(const KParams& p)
 {
-    using geo = Geo<R, (TEAMS > 1)>;
+    using geo = Geo<R, DENSE>;
     const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
-    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)p.table_bytes +
+    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.off_dct : p.table_bytes) +
                (size_t)TEAMS * ((size_t)p.n_dst + n_lq + 3) * geo::SLOTS * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
-constexpr int64_t kTeamsMinPairs = 24576;      // measured crossover: ~1600 one-second clips (tools/sweep.py)
+constexpr int64_t kTeamsMinPairs = 49152;      // measured crossover vs the 3-CTA variant: ~3300 one-second clips (tools/sweep.py)
+constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 232448;
 
-// Teams per CTA for a configuration: three 8-warp teams (24 warps per SM) for n_fft = 1024 when the tables leave
-// room for it, else one team per CTA and two CTAs per SM.  SCFEAT_TEAMS=1 forces the latter (tuning / A-B runs).
-int teams_for(int r, const KParams& p)
+// Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM,
+// 3 = dense with one three-team CTA per SM.  SCFEAT_VARIANT=0|1|3 forces one (tuning / A-B runs).
+int variant_for(int r, const KParams& p)
 {
-    static const int forced = [] { const char* e = getenv("SCFEAT_TEAMS"); return e ? atoi(e) : 0; }();
-    if (r != 32 || forced == 1) return 1;
-    if (smem_bytes_rt<32, 3>(p) > (size_t)227 * 1024) return 1;
-    // one 768-thread CTA per SM only pays off when every team gets many tiles (a small batch such as the 512-clip
-    // training batch is better balanced by 2 x 148 CTAs of one team each)
-    return (forced == 3 || p.n_pairs >= kTeamsMinPairs) ? 3 : 1;
+    static const int forced = [] { const char* e = getenv("SCFEAT_VARIANT"); return e ? atoi(e) : -1; }();
+    if (r != 32 || forced == 0) return 0;
+    const bool fits3 = smem_bytes_rt<32, 3, true>(p) <= kSmemMaxBlock;
+    const bool fits1 = 3 * (smem_bytes_rt<32, 1, true>(p) + kSmemReserve) <= kSmemPerSm;
+    if (forced == 3 && fits3) return 3;
+    if (forced == 1 && fits1) return 1;
+    if (fits3 && p.n_pairs >= kTeamsMinPairs) return 3;
+    return fits1 ? 1 : 0;
 }
 
 size_t extract_smem_bytes(int r, const KParams& p)
 {
-    if (r == 32) return teams_for(r, p) == 3 ? smem_bytes_rt<32, 3>(p) : smem_bytes_rt<32, 1>(p);
-    return r == 16 ? smem_bytes_rt<16, 1>(p) : smem_bytes_rt<8, 1>(p);
+    if (r == 32) {
+        const int v = variant_for(r, p);
+        return v == 3 ? smem_bytes_rt<32, 3, true>(p) : v == 1 ? smem_bytes_rt<32, 1, true>(p) : smem_bytes_rt<32, 1, false>(p);
+    }
+    return r == 16 ? smem_bytes_rt<16, 1, false>(p) : smem_bytes_rt<8, 1, false>(p);
 }
 
 size_t extract_smem_limit(int r, const KParams& p)
 {
-    return teams_for(r, p) == 3 ? (size_t)227 * 1024 : (size_t)(227 * 1024) / kCtasPerSm - 1024;
+    const int v = variant_for(r, p);
+    return v == 3 ? kSmemMaxBlock : v == 1 ? kSmemPerSm / 3 - kSmemReserve : kSmemPerSm / kCtasPerSm - kSmemReserve;
 }
 
 int pairs_per_tile(int r) { return kWarps * (32 / r); }
 int bank_groups(int r) { return kThreads / (2 * kWarps * (32 / r)); }
 
-template <int R, typename InT, bool FAST, int TEAMS>
+template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
 {
-    auto kern = extract_kernel<R, InT, FAST, TEAMS>;
+    auto kern = extract_kernel<R, InT, FAST, TEAMS, DENSE>;
     static size_t configured[16] = {0};          // per device: the attribute call costs microseconds per launch
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        if (DENSE)       // ask for the largest shared-memory carve-out so that three CTAs (or the big one) fit
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev & 15] = smem;
     }
-    const int64_t ctas_per_sm = TEAMS == 1 ? kCtasPerSm : 1;
+    const int64_t ctas_per_sm = TEAMS == 3 ? 1 : (DENSE ? 3 : kCtasPerSm);
     int64_t grid = (int64_t)num_sms * ctas_per_sm;
     const int64_t need = (n_tiles + TEAMS - 1) / TEAMS;
     if (grid > need) grid = need;
@@ -719,27 +751,30 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
     return cudaGetLastError();
 }
 
-template <int R, int TEAMS>
+template <int R, int TEAMS, bool DENSE>
 static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
                             size_t smem)
 {
     if (is_f32) {
-        return fast ? launch_one<R, float, true, TEAMS>(p, n_tiles, num_sms, st, smem)
-                    : launch_one<R, float, false, TEAMS>(p, n_tiles, num_sms, st, smem);
+        return fast ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                    : launch_one<R, float, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
     }
-    return fast ? launch_one<R, int16_t, true, TEAMS>(p, n_tiles, num_sms, st, smem)
-                : launch_one<R, int16_t, false, TEAMS>(p, n_tiles, num_sms, st, smem);
+    return fast ? launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                : launch_one<R, int16_t, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
 }
 
 cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
                            cudaStream_t st, size_t smem)
 {
     switch (r) {
-        case 32:
-            return teams_for(r, p) == 3 ? launch_r<32, 3>(is_f32, fast, p, n_tiles, num_sms, st, smem)
-                                        : launch_r<32, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        case 16: return launch_r<16, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        case 8: return launch_r<8, 1>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 32: {
+            const int v = variant_for(r, p);
+            if (v == 3) return launch_r<32, 3, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+            if (v == 1) return launch_r<32, 1, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+            return launch_r<32, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        }
+        case 16: return launch_r<16, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 8: return launch_r<8, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
 }
