@@ -1,6 +1,11 @@
 #!/usr/bin/env python3
 """Generates fft_gen.cuh: straight-line in-register complex FFTs (N = 8, 16, 32) for sm_100a.
 
+The header holds the PACKED forms (emit_fft_packed: f32x2 instructions on (re, im) register pairs).  The scalar
+emitters (emit_fft, emit_fft_tw) are kept as the readable derivation of the same butterflies and are what the packed
+forms were checked against; they are not emitted any more.
+
+
 Radix-2 decimation-in-time, fully unrolled, twiddles as float literals.  Input is expected in
 bit-reversed order (the caller permutes for free: every index is a compile-time constant, so the
 arrays live in registers); output is in natural order.
@@ -164,11 +169,6 @@ def main():
     print('    for (int b = 0; b < bits; ++b) r = (r << 1) | ((i >> b) & 1);')
     print('    return r;')
     print('}')
-    print()
-    for n in (8, 16, 32):
-        print(emit_fft(n))
-        print()
-    print(emit_fft_tw(32))
     print()
     print('#include "f32x2.cuh"')
     print()

@@ -26,9 +26,6 @@
 
 namespace scf {
 
-#ifndef SCF_MIN_CTAS
-#define SCF_MIN_CTAS kCtasPerSm
-#endif
 
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
 
@@ -184,7 +181,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
 //   TEAMS = 3: one 768-thread CTA of three independent teams that share one table copy and synchronise through their
 //              own named barriers -- large jobs.
 template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
-__global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 : SCF_MIN_CTAS))
+__global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 : kCtasPerSm))
     extract_kernel(const KParams p, const uint32_t n_tiles)
 {
     static_assert(TEAMS == 1 || DENSE, "multi-team CTAs need the dense layout");
@@ -278,12 +275,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
     // of the current tile run (those need few registers), so the FFT stage never waits on HBM
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead)
-#ifdef SCF_NO_REG_PREFETCH
-    constexpr bool kPrefetch = false;
-#else
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;
-#endif
-        // (24-warp CTAs have no registers to spare)
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;     // (24-warp CTAs have no registers to spare)
     InT raw[geo::G][geo::NLOAD];
     auto prefetch = [&](uint32_t tile) {
         if constexpr (kPrefetch) {
