@@ -66,11 +66,6 @@ struct KParams {
     uint32_t ppc_magic, ppc_shift;   // fast division by pairs_per_clip
 };
 
-struct LaunchGeom {
-    int grid;
-    size_t smem;
-};
-
 // scfeat_kernels.cu
 cudaError_t launch_extract(int radix_r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles,
                            int num_sms, cudaStream_t st, size_t smem_bytes);
@@ -78,7 +73,6 @@ size_t extract_smem_bytes(int radix_r, const KParams& p);
 size_t extract_smem_limit(int radix_r, const KParams& p);
 int pairs_per_tile(int radix_r);
 int bank_groups(int radix_r);
-cudaError_t prepare_kernels(int device);
 
 // streaming helpers (scfeat_kernels.cu)
 struct StreamState {

@@ -771,8 +771,6 @@ cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int6
     }
 }
 
-cudaError_t prepare_kernels(int) { return cudaSuccess; }
-
 // ------------------------------------------------------------------------------------------------
 // Streaming state machine of Listener.update_vectors (listen.py:96-114) for n_streams listeners.
 //   append : window_audio = concat(window_audio, chunk)                       (listen.py:101)
