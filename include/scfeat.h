@@ -106,6 +106,13 @@ int scf_build_bank(const scf_config* cfg, double* bank_out);
  * inference/tflite/mfcc.h:42-71. */
 int scf_build_dct(int32_t n_filt, int32_t n_coeffs, double* dct_out);
 
+/* Test hook (host only, no GPU): evaluates the filterbank through the kernel's own work list -- the dense bank cut
+ * into two-filter tasks, runs and partial sums exactly as the bank phase walks them -- for one frame pair with power
+ * spectra power_a / power_b [n_fft/2+1].  sums_a / sums_b [n_filt] must equal bank @ power.
+ * stats4 (nullable): {tasks, partial-sum rows, thread groups, longest group list}. */
+int scf_bank_apply_tasks(const scf_config* cfg, const double* power_a, const double* power_b, double* sums_a,
+                         double* sums_b, int32_t* stats4);
+
 /* ---- plan ------------------------------------------------------------------------------ */
 
 /* Builds bank / DCT / twiddle / window tables in float64 on the host, uploads them.

@@ -25,6 +25,7 @@ PAD_FRONT_ZERO, PAD_NONE = 0, 1
 
 EXPORTS = [
     'scf_config_default', 'scf_num_frames', 'scf_out_cols', 'scf_build_bank', 'scf_build_dct',
+    'scf_bank_apply_tasks',
     'scf_plan_create', 'scf_plan_destroy', 'scf_plan_config',
     'scf_extract_i16', 'scf_extract_f32', 'scf_extract_host_i16', 'scf_extract_host_f32',
     'scf_extract_host_i16_async', 'scf_host_sync',
@@ -89,6 +90,7 @@ def lib():
         L.scf_out_cols.restype = i32
         L.scf_build_bank.argtypes = [cfgp, vp]
         L.scf_build_dct.argtypes = [i32, i32, vp]
+        L.scf_bank_apply_tasks.argtypes = [cfgp, vp, vp, vp, vp, vp]
         L.scf_plan_create.argtypes = [cfgp, ctypes.POINTER(vp)]
         L.scf_plan_destroy.argtypes = [vp]
         L.scf_plan_destroy.restype = None
@@ -157,6 +159,20 @@ def build_dct(n_filt, n_coeffs):
     out = np.zeros((n_filt, min(n_filt, n_coeffs)), dtype=np.float64)
     check(lib().scf_build_dct(n_filt, n_coeffs, out.ctypes.data))
     return out
+
+
+def bank_apply_tasks(power_a, power_b, **kw):
+    """Filterbank sums of one frame pair through the kernel's task list, on the host (test hook).
+    Returns (sums_a, sums_b, stats) with stats = dict(tasks, partial_rows, groups, longest_group)."""
+    c, keep = make_config(**kw)
+    pa = np.ascontiguousarray(power_a, dtype=np.float64)
+    pb = np.ascontiguousarray(power_b, dtype=np.float64)
+    assert pa.shape == pb.shape == (c.n_fft // 2 + 1,)
+    sa, sb = np.zeros(c.n_filt), np.zeros(c.n_filt)
+    st = np.zeros(4, dtype=np.int32)
+    check(lib().scf_bank_apply_tasks(ctypes.byref(c), pa.ctypes.data, pb.ctypes.data, sa.ctypes.data, sb.ctypes.data,
+                                     st.ctypes.data))
+    return sa, sb, dict(zip(('tasks', 'partial_rows', 'groups', 'longest_group'), (int(v) for v in st)))
 
 
 def num_frames(n_samples, window, hop):

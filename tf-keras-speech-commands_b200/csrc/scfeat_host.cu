@@ -229,61 +229,91 @@ static int upload(T** dptr, const std::vector<T>& host)
     return SCF_OK;
 }
 
-// Turns the dense float64 bank into the bank phase's work list: every quantity (filter, or the frame
-// energy) is cut into tasks of kTaskBins consecutive bins; consecutive tasks form runs; runs are spread over
-// the thread groups (longest-processing-time first) so that every group has about the same number of tasks.
+// Turns the dense float64 bank into the bank phase's work list (format: scfeat_internal.h).
+//  1. The bin axis is cut at every filter's first and one-past-last non-zero bin: inside such a segment the set of
+//     active filters is constant (two for a triangular mel bank, about four for the Bark bank).
+//  2. The active filters of a segment are taken two at a time; each filter pair covers the segment with tasks of
+//     kTaskBins bins (first bin even, pulled back at the end of the row, zero weights outside the segment).
+//  3. The tasks of one (segment, filter pair) form a run that accumulates in registers; long runs are split so that no
+//     run exceeds the per-group average, and runs are spread over the thread groups longest first.
+//  4. Every (run, filter) owns a partial-sum row; rows are numbered so that each filter's rows are consecutive.
 struct TaskList {
-    std::vector<uint32_t> words;        // grouped task words (see scfeat_internal.h)
-    std::vector<int32_t> begin;         // [n_groups + 1]
-    std::vector<double> weights;        // kTaskBins doubles per task, same order as `words`
-    std::vector<QSpec> qspec;           // per quantity: its runs' partial-sum slots
-    int n_dst = 0;
+    std::vector<uint32_t> words;        // grouped task words
+    std::vector<int32_t> begin;         // [n_groups][2]: first and one past the last task of the group
+    std::vector<double> weights;        // 2 * kTaskBins doubles per task, same order as `words`
+    std::vector<QSpec> qspec;           // per filter: its partial-sum rows
+    int n_dst = 0;                      // partial-sum rows in use (row n_dst is the dump row)
 };
 
-static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins, bool with_energy, int n_groups,
-                        TaskList& tl)
+static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins, int radix_r, int n_groups, TaskList& tl)
 {
-    struct Task { int q, k0; };
-    struct Run { int q; std::vector<Task> tasks; };
-    const int n_q = n_filt + (with_energy ? 1 : 0);
-    const int row_end = ((n_bins - 1) + 4);            // power rows hold n_fft/2 + 4 floats
-    std::vector<std::vector<Task>> per_q(n_q);
-    int total = 0;
-    for (int q = 0; q < n_q; ++q) {
-        int lo = n_bins, hi = -1;
-        if (q < n_filt) {
-            for (int k = 0; k < n_bins; ++k)
-                if (bank[(size_t)q * n_bins + k] != 0.0) { lo = std::min(lo, k); hi = std::max(hi, k); }
-        } else {
-            lo = 0; hi = n_bins - 1;
-        }
-        if (hi < 0) { lo = 0; hi = 0; }                 // empty filter: one all-zero task so that its sum is written
-        for (int k0 = lo & ~3; k0 <= hi; k0 += kTaskBins) per_q[q].push_back({q, std::min(k0, row_end - kTaskBins)});
-        total += (int)per_q[q].size();
+    struct Run { int fa, fb, seg_lo, seg_hi; std::vector<int> k0; int da = 0, db = 0; };
+    const int row_bins = pair_row_bins(radix_r);
+    auto W = [&](int f, int k) { return (f >= 0 && k < n_bins) ? bank[(size_t)f * n_bins + k] : 0.0; };
+    // 1. segments
+    std::vector<int> lo(n_filt, n_bins), hi(n_filt, -1);
+    std::vector<int> cuts;
+    for (int f = 0; f < n_filt; ++f) {
+        for (int k = 0; k < n_bins; ++k)
+            if (W(f, k) != 0.0) { lo[f] = std::min(lo[f], k); hi[f] = std::max(hi[f], k); }
+        if (hi[f] >= 0) { cuts.push_back(lo[f]); cuts.push_back(hi[f] + 1); }
     }
-    const int cap = std::max(1, (total + n_groups - 1) / n_groups);      // tasks per run at most
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    // 2. runs (one per segment and filter pair), tasks of kTaskBins bins
+    std::vector<Run> whole;
+    int total = 0;
+    for (size_t s = 0; s + 1 < cuts.size(); ++s) {
+        const int a = cuts[s], b = cuts[s + 1];
+        std::vector<int> act;
+        for (int f = 0; f < n_filt; ++f)
+            if (hi[f] >= 0 && lo[f] <= a && b <= hi[f] + 1) act.push_back(f);
+        for (size_t i = 0; i < act.size(); i += 2) {
+            Run r;
+            r.fa = act[i];
+            r.fb = (i + 1 < act.size()) ? act[i + 1] : -1;
+            r.seg_lo = a;
+            r.seg_hi = b;
+            for (int k0 = a & ~1; k0 < b; k0 += kTaskBins) r.k0.push_back(std::min(k0, row_bins - kTaskBins));
+            total += (int)r.k0.size();
+            whole.push_back(r);
+        }
+    }
+    // 3. split long runs, spread over the groups
+    const int cap = std::max(1, (total + n_groups - 1) / n_groups);
     std::vector<Run> runs;
-    tl.qspec.assign(n_q, QSpec{0, 0});
-    for (int q = 0; q < n_q; ++q) {
-        const int n = (int)per_q[q].size();
+    for (const Run& r : whole) {
+        const int n = (int)r.k0.size();
         const int pieces = (n + cap - 1) / cap;
-        tl.qspec[q].dst0 = (int)runs.size();
-        tl.qspec[q].count = pieces;
         int done = 0;
         for (int pc = 0; pc < pieces; ++pc) {
             const int len = (n - done + (pieces - pc) - 1) / (pieces - pc);
-            Run r;
-            r.q = q;
-            r.tasks.assign(per_q[q].begin() + done, per_q[q].begin() + done + len);
-            runs.push_back(r);
+            Run x = r;
+            x.k0.assign(r.k0.begin() + done, r.k0.begin() + done + len);
+            // a piece owns the bins from its first task up to the next piece's first task
+            if (pc > 0) x.seg_lo = std::max(r.seg_lo, r.k0[done]);
+            if (pc + 1 < pieces) x.seg_hi = std::min(r.seg_hi, r.k0[done + len]);
+            runs.push_back(x);
             done += len;
         }
     }
-    tl.n_dst = (int)runs.size();
+    // 4. partial-sum rows, consecutive per filter
+    tl.qspec.assign(n_filt, QSpec{0, 0});
+    int next = 0;
+    for (int f = 0; f < n_filt; ++f) {
+        tl.qspec[f].dst0 = next;
+        for (Run& r : runs) {
+            if (r.fa == f) r.da = next++;
+            if (r.fb == f) r.db = next++;
+        }
+        tl.qspec[f].count = next - tl.qspec[f].dst0;
+    }
+    tl.n_dst = next;
+    for (Run& r : runs)
+        if (r.fb < 0) r.db = tl.n_dst;                  // dump row
     std::vector<size_t> order(runs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(),
-                     [&](size_t a, size_t b) { return runs[a].tasks.size() > runs[b].tasks.size(); });
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return runs[a].k0.size() > runs[b].k0.size(); });
     std::vector<std::vector<size_t>> per_group(n_groups);
     std::vector<int> load(n_groups, 0);
     for (size_t idx : order) {
@@ -291,46 +321,67 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
         for (int g = 1; g < n_groups; ++g)
             if (load[g] < load[best]) best = g;
         per_group[best].push_back(idx);
-        load[best] += (int)runs[idx].tasks.size();
+        load[best] += (int)runs[idx].k0.size();
     }
-    // a bin may be covered by two tasks of the same quantity only where the last task was pulled back to stay
-    // inside the row; `covered` makes sure its weight is applied once
     tl.words.clear();
     tl.weights.clear();
-    tl.begin.assign(n_groups + 1, 0);
-    std::vector<std::vector<char>> covered(n_q, std::vector<char>(row_end, 0));
-    // weights must be decided in quantity order (not group order) so that "first task wins" is well defined
-    std::vector<std::vector<std::vector<double>>> w_of(runs.size());
-    for (size_t r = 0; r < runs.size(); ++r) {
-        w_of[r].resize(runs[r].tasks.size());
-        for (size_t t = 0; t < runs[r].tasks.size(); ++t) {
-            const Task& tk = runs[r].tasks[t];
-            std::vector<double>& w = w_of[r][t];
-            w.assign(kTaskBins, 0.0);
-            for (int i = 0; i < kTaskBins; ++i) {
-                const int k = tk.k0 + i;
-                if (k >= n_bins || covered[tk.q][k]) continue;
-                covered[tk.q][k] = 1;
-                w[i] = (tk.q < n_filt) ? bank[(size_t)tk.q * n_bins + k] : 1.0;
-            }
-        }
-    }
+    tl.begin.assign(2 * n_groups, 0);
     for (int g = 0; g < n_groups; ++g) {
-        tl.begin[g] = (int32_t)tl.words.size();
-        for (size_t r : per_group[g])
-            for (size_t t = 0; t < runs[r].tasks.size(); ++t) {
-                uint32_t word = (uint32_t)runs[r].tasks[t].k0 | ((uint32_t)r << 12);
-                if (t + 1 == runs[r].tasks.size()) word |= 0x80000000u;
+        tl.begin[2 * g] = (int32_t)tl.words.size();
+        for (size_t ri : per_group[g]) {
+            const Run& r = runs[ri];
+            int covered_to = r.seg_lo;                  // bins below this one already have their weight in a task
+            for (size_t t = 0; t < r.k0.size(); ++t) {
+                uint32_t word = (uint32_t)(2 * r.k0[t]);
+                if (t + 1 == r.k0.size()) word |= 0x80000000u | ((uint32_t)r.da << 12) | ((uint32_t)r.db << 21);
                 tl.words.push_back(word);
-                tl.weights.insert(tl.weights.end(), w_of[r][t].begin(), w_of[r][t].end());
+                for (int i = 0; i < kTaskBins; ++i) {
+                    const int k = r.k0[t] + i;
+                    const bool mine = k >= covered_to && k < r.seg_hi;
+                    tl.weights.push_back(mine ? W(r.fa, k) : 0.0);
+                    tl.weights.push_back(mine ? W(r.fb, k) : 0.0);
+                }
+                covered_to = std::max(covered_to, std::min(r.seg_hi, r.k0[t] + kTaskBins));
             }
-        // the kernel consumes two tasks per iteration (8-byte aligned pairs): pad with a null task
-        if ((tl.words.size() - (size_t)tl.begin[g]) & 1) {
-            tl.words.push_back(0u);
-            tl.weights.insert(tl.weights.end(), kTaskBins, 0.0);
+        }
+        tl.begin[2 * g + 1] = (int32_t)tl.words.size();
+    }
+}
+
+// The task list evaluated on the host in the order the kernel's bank phase walks it (test hook for the decomposition;
+// pair_row holds (A[k], B[k]) interleaved like the kernel's shared-memory row).
+static void apply_tasks(const TaskList& tl, int n_groups, const std::vector<double>& pair_row, std::vector<double>& sums_a,
+                        std::vector<double>& sums_b)
+{
+    std::vector<double> pa(tl.n_dst + 1, 0.0), pb(tl.n_dst + 1, 0.0);
+    for (int g = 0; g < n_groups; ++g) {
+        double aa = 0, ab = 0, ba = 0, bb = 0;          // (filter a | b) x (frame A | B)
+        for (int t = tl.begin[2 * g]; t < tl.begin[2 * g + 1]; ++t) {
+            const uint32_t w = tl.words[t];
+            const int off = (int)(w & 0xfffu);
+            for (int i = 0; i < kTaskBins; ++i) {
+                const double wa = tl.weights[(size_t)t * 2 * kTaskBins + 2 * i];
+                const double wb = tl.weights[(size_t)t * 2 * kTaskBins + 2 * i + 1];
+                aa += wa * pair_row[off + 2 * i];
+                ab += wa * pair_row[off + 2 * i + 1];
+                ba += wb * pair_row[off + 2 * i];
+                bb += wb * pair_row[off + 2 * i + 1];
+            }
+            if (w & 0x80000000u) {
+                const int da = (w >> 12) & 0x1ff, db = (w >> 21) & 0x1ff;
+                pa[da] = aa; pb[da] = ab;
+                pa[db] = ba; pb[db] = bb;
+                aa = ab = ba = bb = 0;
+            }
         }
     }
-    tl.begin[n_groups] = (int32_t)tl.words.size();
+    sums_a.assign(tl.qspec.size(), 0.0);
+    sums_b.assign(tl.qspec.size(), 0.0);
+    for (size_t f = 0; f < tl.qspec.size(); ++f)
+        for (int j = 0; j < tl.qspec[f].count; ++j) {
+            sums_a[f] += pa[tl.qspec[f].dst0 + j];
+            sums_b[f] += pb[tl.qspec[f].dst0 + j];
+        }
 }
 
 // Hacker's Delight unsigned division by an invariant (round-up method); magic == 0 marks a power of two.
@@ -422,7 +473,12 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         build_bank(cfg, bank);
         const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
         // (the frame energy -- c0 of the cepstrum -- is summed in the FFT stage, not as a bank row)
-        build_tasks(bank, cfg->n_filt, p->n_bins, false, bank_groups(p->radix_r), tl);
+        build_tasks(bank, cfg->n_filt, p->n_bins, p->radix_r, bank_groups(p->radix_r), tl);
+        if (tl.n_dst + 1 > partial_rows(p->radix_r)) {
+            free_plan_tables(p);
+            delete p;
+            return fail(SCF_ERR_INVALID, "filterbank needs more partial sums than the kernel's shared memory holds");
+        }
         p->n_tasks = (int)tl.words.size();
         p->n_q = cfg->n_filt + (cep ? 1 : 0);
         p->n_dst = tl.n_dst;
@@ -445,7 +501,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     p->off_qspec = (int)align16(p->off_tbeg + tl.begin.size() * 4);
     p->table_small_bytes = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
     p->off_wts = p->table_small_bytes;
-    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * kTaskBins * 4);
+    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * 2 * kTaskBins * 4);
     p->table_bytes = (int)align16(p->off_dct + dct_t.size() * 4);
     for (int variant = 0; variant < 2; ++variant) {
         const double ps = variant == 0 ? ps_i16 : ps_f32;
@@ -781,6 +837,39 @@ int scf_build_bank(const scf_config* cfg, double* bank_out)
     std::vector<double> bank;
     build_bank(&c, bank);
     memcpy(bank_out, bank.data(), bank.size() * sizeof(double));
+    return SCF_OK;
+}
+
+int scf_bank_apply_tasks(const scf_config* cfg, const double* power_a, const double* power_b, double* sums_a,
+                         double* sums_b, int32_t* stats4)
+{
+    scf_config c;
+    if (!cfg || !power_a || !power_b || !sums_a || !sums_b) return fail(SCF_ERR_INVALID, "NULL argument");
+    c = *cfg;
+    if (c.output == SCF_OUT_POWER) c.output = SCF_OUT_LOG_BANK;
+    int rc = check_config(&c);
+    if (rc) return rc;
+    const int r = c.n_fft / 32, n_bins = c.n_fft / 2 + 1, n_groups = bank_groups(r);
+    std::vector<double> bank;
+    build_bank(&c, bank);
+    TaskList tl;
+    build_tasks(bank, c.n_filt, n_bins, r, n_groups, tl);
+    // the kernel's pair row: (A[k], B[k]) interleaved, bins 0 .. n_fft/2 + 1, the last one a pad.  The pad and the
+    // bins a task touches outside its segment must carry zero weight: poison them with NaN-free but huge values
+    std::vector<double> row((size_t)pair_row_floats(r), 1e300);
+    for (int k = 0; k < n_bins; ++k) { row[2 * k] = power_a[k]; row[2 * k + 1] = power_b[k]; }
+    std::vector<double> sa, sb;
+    apply_tasks(tl, n_groups, row, sa, sb);
+    memcpy(sums_a, sa.data(), sa.size() * sizeof(double));
+    memcpy(sums_b, sb.data(), sb.size() * sizeof(double));
+    if (stats4) {
+        int worst = 0;
+        for (int g = 0; g < n_groups; ++g) worst = std::max(worst, tl.begin[2 * g + 1] - tl.begin[2 * g]);
+        stats4[0] = (int32_t)tl.words.size();
+        stats4[1] = tl.n_dst;
+        stats4[2] = n_groups;
+        stats4[3] = worst;
+    }
     return SCF_OK;
 }
 

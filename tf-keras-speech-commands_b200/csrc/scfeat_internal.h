@@ -14,12 +14,21 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kCtasPerSm = 16 / kWarps;    // 16 warps per SM at <= 128 registers per thread
 constexpr int kMaxPeers = 8;
 
-// Bank-phase task word: a run of exactly 16 consecutive bins (4 float4) of one filter.
-//   bits  0..11  first bin (multiple of 4)
-//   bits 12..23  partial-sum slot the run is stored to
-//   bit  31      last task of its run: store the accumulated sum
-// The 16 weights of task t sit at float4 index 4*t of the weight table (same order as the tasks).
-constexpr int kTaskBins = 16;
+// Bank phase.  The power spectra of a frame PAIR sit in one shared-memory row, interleaved per bin as
+// (|A[k]|^2, |B[k]|^2), bins 0 .. n_fft/2 + 1 (the last one is a zero pad).  A task is a run of kTaskBins consecutive
+// bins (first bin even -> 16-byte aligned) applied to TWO filters at once, so every power value is read once per
+// filter pair and all the arithmetic is packed (FFMA2 on the (A, B) pair with a broadcast weight).
+// Task word:
+//   bits  0..11  float offset of the first bin inside the pair row ( = 2 * first bin, multiple of 4)
+//   bits 12..20  partial-sum row of the first filter      } only read when bit 31 is set
+//   bits 21..29  partial-sum row of the second filter     }
+//   bit  31      last task of its run: store the two accumulated sums
+// The 16 weights of task t sit at float4 index 4*t of the weight table, as (a[k], b[k], a[k+1], b[k+1]) per float4.
+constexpr int kTaskBins = 8;
+constexpr int pair_row_bins(int r) { return 16 * r + 2; }
+constexpr int pair_row_floats(int r) { return 2 * pair_row_bins(r); }
+// partial-sum rows every kernel layout can hold (they live in the tails of the warps' exchange regions, see Geo)
+constexpr int partial_rows(int r) { return r == 32 ? 496 : r == 16 ? 304 : 184; }
 
 // Which partial sums make up output quantity q (filter q, or the frame energy for q == n_filt).
 struct QSpec {
@@ -51,7 +60,7 @@ struct KParams {
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
     float zero_energy;           // int16 input: frame energies below this mean "every sample was zero"
     // tables: one device blob, copied verbatim into shared memory by a single TMA bulk copy
-    //   [twiddles float4[4][32] + float4[32]] [tasks u32[n_tasks]] [task_begin i32[n_groups+1]] [qspec int2[n_filt]]
+    //   [twiddles float4[4][32] + float4[32]] [tasks u32[n_tasks]] [task ranges int2[n_groups]] [qspec int2[n_filt]]
     //   [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]                 (every section 16-byte aligned)
     const void* tables;
     int32_t table_bytes;         // whole blob
@@ -59,7 +68,7 @@ struct KParams {
     int32_t off_wts, off_dct, off_tasks, off_tbeg, off_qspec;
     int32_t n_tasks;
     int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)
-    int32_t n_dst;               // number of partial-sum slots
+    int32_t n_dst;               // number of partial-sum rows (row n_dst is a dump row for unpaired filters)
     int32_t n_filt;
     int32_t n_filt4;             // n_filt rounded up to a multiple of 4
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)

@@ -29,29 +29,41 @@ namespace scf {
 
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
 
-// SWZ = false: exchange rows are padded by 16 bytes (conflict-free without address arithmetic), the power rows sit
-//               behind the mirror buffers; 8704 bytes per warp at n_fft = 1024.
-// SWZ = true : exchange rows are unpadded and XOR-swizzled at float4 granularity, the power rows reuse the mirror
-//               buffers' space; exactly 8192 bytes per warp, which lets 24 warps share one SM (see TEAMS).
+// SWZ = false: exchange rows are padded by 16 bytes (conflict-free without address arithmetic); 8704 bytes per warp at
+//               n_fft = 1024.
+// SWZ = true : exchange rows are unpadded and XOR-swizzled at float4 granularity; exactly 8192 bytes per warp, which
+//               lets 24 warps share one SM (see TEAMS).
+// After pass 2 the warp's exchange region is free: its head takes the power rows of the warp's pairs (one row per
+// PAIR, the two frames interleaved as (|A[k]|^2, |B[k]|^2) so that the bank phase works on packed values), its tail
+// takes a share of the team's partial-sum rows.
 template <int R, bool SWZ = false>
 struct Geo {
     static constexpr int NFFT = 32 * R;
     static constexpr int NB = 16 * R;                 // highest bin index (n_fft / 2)
     static constexpr int LOG2R = (R == 32) ? 5 : (R == 16) ? 4 : 3;
     static constexpr int G = 32 / R;                  // frame pairs per warp
-    static constexpr int PPT = kWarps * G;            // pairs per tile (one tile = one team's 8 warps)
-    static constexpr int SLOTS = 2 * PPT;             // frame slots per tile
-    static constexpr int NGRP = kThreads / SLOTS;     // bank-phase thread groups
+    static constexpr int PPT = kWarps * G;            // pairs per tile (one tile = one team's 8 warps) = bank-phase slots
+    static constexpr int NGRP = kThreads / PPT;       // bank-phase thread groups
     static constexpr int XROW = SWZ ? 2 * R : 2 * R + 4;   // floats per exchange row
     static constexpr int XPAIR = 32 * XROW;
     static constexpr int XWARP = G * XPAIR;           // floats of shared memory owned by one warp
-    static constexpr int MIR = 2 * NB + 4;            // floats per pair: upper half of Z (+1 slot for Z[0])
-    static constexpr int PROW = NB + 4;               // floats per power row ( = 4 mod 32 -> conflict-free float4 columns)
-    static constexpr int P_OFF = SWZ ? 0 : G * MIR;   // power rows: behind the mirror buffers, or on top of them
+    static constexpr int PROW2 = pair_row_floats(R);  // floats per pair row ( = 4 mod 32 -> conflict-free float4 columns)
+    static constexpr int P_FREE = G * PROW2 + 28;     // first float behind the (skewed) power rows
+    static constexpr int DROW = 2 * PPT;              // floats per partial-sum row: one packed (A, B) value per slot
+    static constexpr int DROWS = (XWARP - P_FREE) / DROW;   // partial-sum rows per warp region
     static constexpr int NLOAD = R + R / 2;           // fast path: strided samples per lane covering both frames
-    static_assert(P_OFF + 2 * G * PROW + 32 <= XWARP && G * MIR <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(P_FREE % 4 == 0 && P_FREE <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(kWarps * DROWS >= partial_rows(R), "partial-sum rows promised to the host must fit");
     static_assert(!SWZ || R == 32, "the swizzled layout is written for n_fft = 1024");
 };
+
+// shared-memory floats per team outside the exchange area (see the carve-up in the kernel)
+template <int PPT>
+__host__ __device__ inline int team_smem_floats(const KParams& p)
+{
+    const int n_lq = p.n_q > p.n_filt4 ? p.n_q : p.n_filt4;
+    return 2 * PPT * (n_lq + 1) + (p.n_peers != 0 ? 2 * PPT * (p.out_cols + 2) : 0);
+}
 
 __device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -208,10 +220,12 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    const int team_floats = (p.n_dst + n_lq + 3) * geo::SLOTS;      // partial sums, log bands, row ids (int64), frame energies
-    float* s_part = reinterpret_cast<float*>(s_tab + staged_bytes) + team * team_floats;
-    float* s_logq = s_part + p.n_dst * geo::SLOTS;
-    float* s_energy = s_logq + (n_lq + 2) * geo::SLOTS;              // [slot] frame energy, written by the FFT stage
+    // per team: log bands [n_lq][slot] and frame energies [slot] as packed (A, B) pairs; with the fused all-gather
+    // also the finished rows [frame slot][col] and their row ids (int64)
+    const int team_floats = team_smem_floats<geo::PPT>(p);
+    f2* s_logq = reinterpret_cast<f2*>(reinterpret_cast<float*>(s_tab + staged_bytes) + team * team_floats);
+    f2* s_energy = s_logq + n_lq * geo::PPT;                          // written by the FFT stage
+    float* s_stage = reinterpret_cast<float*>(s_energy + geo::PPT);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + staged_bytes) + TEAMS * team_floats);
     float* xw = s_xch + warp * geo::XWARP;
     auto team_sync = [&]() {
@@ -232,34 +246,29 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         mbar_init(s_bar, 1);
         bulk_g2s(s_tab, p.tables, (uint32_t)staged_bytes, s_bar);
     }
-    if constexpr (!SWZ) {
-        // the 16-byte pad of every exchange row is never written by pass 1 but aliases power-row words that the
-        // bank phase multiplies by zero weights: it must not hold NaN bit patterns
-#pragma unroll
-        for (int g = 0; g < geo::G; ++g)
-            *reinterpret_cast<float4*>(xw + g * geo::XPAIR + lane * geo::XROW + 2 * R) = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-        // unpadded rows: pass 1 rewrites the whole region every tile, but a warp that never runs a pass 1 (tail) must
-        // not leave NaN patterns where the bank phase reads
-        for (int i = lane; i < geo::XWARP / 4; i += 32) reinterpret_cast<float4*>(xw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int i = tid; i < n_lq * geo::SLOTS; i += kThreads) s_logq[i] = 0.f;
+    // (no zero fill of the exchange area: every float of a valid pair row is rewritten each tile, and whatever an
+    //  unused slot holds only reaches that slot's own, discarded, results)
+    for (int i = tid; i < n_lq * geo::PPT; i += kThreads) s_logq[i] = pk(0.f, 0.f);
 
     // pass-2 role of this lane: pair g2 of the warp, column k1
     const int g2 = lane / R;
     const int k1 = lane % R;
-    // power rows of this warp: skewed so that the bank phase's float4 column reads are conflict-free
-    float* pw = xw + geo::P_OFF + 4 * ((2 * geo::G * warp) & 7);
+    // power rows of this warp's pairs: skewed so that the bank phase's float4 column reads are conflict-free
+    // (row of slot s starts at 4 * (s & 7) mod 32 words; a quarter warp reads 8 consecutive slots)
+    float* pw = xw + 4 * ((geo::G * warp) & 7);
 
-    // bank / epilogue role of this thread
-    const int slot = tid % geo::SLOTS;
-    const int grp = tid / geo::SLOTS;
+    // bank / epilogue role of this thread: pair slot `slot`, thread group `grp`
+    const int slot = tid % geo::PPT;
+    const int grp = tid / geo::PPT;
     const float* prow_slot;
     {
-        const int sw = slot / (2 * geo::G);          // warp that produced this slot
-        const int ls = slot % (2 * geo::G);
-        prow_slot = s_xch + sw * geo::XWARP + geo::P_OFF + 4 * ((2 * geo::G * sw) & 7) + ls * geo::PROW;
+        const int sw = slot / geo::G;                // warp that produced this slot
+        prow_slot = s_xch + sw * geo::XWARP + 4 * ((geo::G * sw) & 7) + (slot % geo::G) * geo::PROW2;
     }
+    // partial-sum row d of this team, this thread's slot
+    auto part = [&](int d) -> f2* {
+        return reinterpret_cast<f2*>(s_xch + (d & 7) * geo::XWARP + geo::P_FREE + (d >> 3) * geo::DROW) + slot;
+    };
 
     // How exactly-zero frames are recognised (they must produce exactly zero power, see the FFT stage):
     //  * fast int16 path with a bank: from the frame energy in the epilogue -- a non-zero int16 frame has raw
@@ -426,37 +435,30 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             }
             __syncwarp();    // every lane has read its column: the region may now be reused
 
-            // ---- separate the two frames: upper half of Z through shared memory ---------------------
-            f2* mir = reinterpret_cast<f2*>(xw + g2 * geo::MIR);
-#pragma unroll
-            for (int k2 = 16; k2 < 32; ++k2) mir[k1 + R * k2 - geo::NB] = y[k2];
-            mir[k1 == 0 ? geo::NB : geo::NB + 1] = y[0];                            // Z[N] == Z[0]; NB+1 is a dump slot
-            __syncwarp();
+            // ---- separate the two frames ------------------------------------------------------------
+            // Z[N - k] for k = k1 + R k2 sits in lane (R - k1) % R of the same pair, register 31 - k2 (k1 == 0: the
+            // lane's own register 32 - k2): a fixed lane permutation, done with shuffles -- one SHFL moves what takes
+            // an STS plus an LDS wavefront through shared memory (tools/microbench/shfl_vs_lds.cu: 33 vs 65 cycles).
             // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
             if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
-            float* pa_row = pw + (2 * g2) * geo::PROW;
-            float* pb_row = pa_row + geo::PROW;
-            f2 mv[16];
+            float* prow = pw + g2 * geo::PROW2;
+            const int src_lane = (lane & ~(R - 1)) | ((R - k1) & (R - 1));
             f2 esum = pk(0.f, 0.f);
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) mv[k2] = mir[geo::NB - (k1 + R * k2)];    // Z[N - k]
-            if constexpr (SWZ) __syncwarp();          // the power rows overwrite the mirror buffers
-#pragma unroll
             for (int k2 = 0; k2 < 16; ++k2) {
-                const int k = k1 + R * k2;
-                const f2 m = mv[k2];
+                f2 m = __shfl_sync(0xffffffffu, y[31 - k2], src_lane);               // Z[N - k]
+                if (k1 == 0) m = y[(32 - k2) & 31];                                  // (Z[N] == Z[0])
                 // 2A[k] = Z + conj(Zm) = (yr + mr, yi - mi);  2B[k] = (yi + mi, mr - yr)
                 const f2 u1 = add2(y[k2], m);                                        // (yr + mr, yi + mi) = (Re 2A, Re 2B)
                 const f2 u2 = add2(mul_mi(y[k2]), mul_i(m));                         // (yi - mi, mr - yr) = (Im 2A, Im 2B)
                 const f2 pp = fma2(u2, u2, mul2(u1, u1));                            // (|2A|^2, |2B|^2)
-                pa_row[k] = lo(pp);
-                pb_row[k] = hi(pp);
+                *reinterpret_cast<f2*>(prow + 2 * (k1 + R * k2)) = pp;
                 esum = add2(esum, pp);
             }
             if (k1 == 0) {                                                           // bin n_fft/2 mirrors onto itself
                 const f2 pp = mul2(mul2(y[16], y[16]), bc(4.f));
-                pa_row[geo::NB] = lo(pp);
-                pb_row[geo::NB] = hi(pp);
+                // ... and bin n_fft/2 + 1 is the row's zero pad (tasks may read it, with zero weights)
+                *reinterpret_cast<ulonglong2*>(prow + 2 * geo::NB) = make_ulonglong2(pp, pk(0.f, 0.f));
                 esum = add2(esum, pp);
             }
             // frame energies (sum of the power row; c0 of the cepstrum, bark_feature.py:173): the values are in
@@ -465,16 +467,15 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             for (int m = R / 2; m >= 1; m >>= 1) esum = add2(esum, __shfl_xor_sync(0xffffffffu, esum, m));
             if (k1 == 0) {
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
-                float* e = s_energy + 2 * (warp * geo::G + g2);
-                e[0] = za ? 0.f : lo(esum) * p.power_scale;
-                e[1] = zb ? 0.f : hi(esum) * p.power_scale;
+                s_energy[warp * geo::G + g2] = pk(za ? 0.f : lo(esum) * p.power_scale, zb ? 0.f : hi(esum) * p.power_scale);
             }
             if (__builtin_expect(zero_mask != 0, 0)) {                     // rare: exact zeros for silent frames
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
+                __syncwarp();
 #pragma unroll 1
                 for (int k = k1; k <= geo::NB; k += R) {                   // a real loop: keep the hot path short
-                    if (za) pa_row[k] = 0.f;
-                    if (zb) pb_row[k] = 0.f;
+                    if (za) prow[2 * k] = 0.f;
+                    if (zb) prow[2 * k + 1] = 0.f;
                 }
             }
         } else {
@@ -490,23 +491,25 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         }
         team_sync();
 
-        // =========================== where this thread's slot goes ==============================
-        int64_t out_row = -1;
+        // =========================== where this thread's pair goes ==============================
+        int64_t row_a = -1;           // output row of frame A; frame B, when present, is the next row
+        bool has_b = false;
         {
-            const uint32_t gp = pair0 + (slot >> 1);
+            const uint32_t gp = pair0 + slot;
             if (gp < n_pairs) {
                 const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                const int f = 2 * (int)(gp - clip * ppc) + (slot & 1);
+                const int f = 2 * (int)(gp - clip * ppc);
                 int nfr = p.frames_per_clip;
                 if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
-                if (f < nfr) out_row = (int64_t)clip * p.frames_per_clip + f;
+                if (f < nfr) row_a = (int64_t)clip * p.frames_per_clip + f;
+                has_b = f + 1 < nfr;
             }
         }
 
         if (p.out_kind == SCF_OUT_POWER) {
             // power_spec(): rows straight out of shared memory, coalesced along the bins;
-            // warp w copies slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
-            for (int s = warp; s < geo::SLOTS; s += kWarps) {
+            // warp w copies frame slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
+            for (int s = warp; s < 2 * geo::PPT; s += kWarps) {
                 const uint32_t gp = pair0 + (s >> 1);
                 int64_t row = -1;
                 if (gp < n_pairs) {
@@ -517,148 +520,152 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     if (f < nfr) row = (int64_t)clip * p.frames_per_clip + f;
                 }
                 if (row < 0) continue;
-                const int sw = s / (2 * geo::G), ls = s % (2 * geo::G);
-                const float* src = s_xch + sw * geo::XWARP + geo::P_OFF + 4 * ((2 * geo::G * sw) & 7) + ls * geo::PROW;
+                const int sw = (s >> 1) / geo::G;
+                const float* src = s_xch + sw * geo::XWARP + 4 * ((geo::G * sw) & 7) + ((s >> 1) % geo::G) * geo::PROW2 + (s & 1);
                 float* dst = p.out + row * p.out_cols;
-                for (int k = lane; k <= geo::NB; k += 32) dst[k] = src[k] * p.power_scale;
+                for (int k = lane; k <= geo::NB; k += 32) dst[k] = src[2 * k] * p.power_scale;
             }
             team_sync();
             continue;
         }
 
         // =========================== bank stage ================================================
-        // tasks are runs of exactly 16 bins (4 float4) of one filter; consecutive tasks of a run accumulate in
-        // registers and the task flagged `last` stores the run's partial sum.  Every group's list is padded to an
-        // even length (null tasks: zero weights), two tasks are in flight per iteration and the next pair of task
-        // words is fetched one iteration ahead, so the shared-memory round trips overlap the FMAs.
+        // tasks are runs of 8 bins applied to two filters at once (see scfeat_internal.h); consecutive tasks of a run
+        // accumulate in registers and the task flagged `last` stores the run's two partial sums.  Two tasks are in
+        // flight per iteration and the next pair of task words is fetched one iteration ahead, so the shared-memory
+        // round trips overlap the FMAs.
         {
-            const int t_end = s_tbeg[grp + 1];
-            int t = s_tbeg[grp];
-            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-            uint2 tk = make_uint2(0u, 0u);
-            if (t < t_end) tk = *reinterpret_cast<const uint2*>(s_tasks + t);
-            for (; t < t_end; t += 2) {
-                const float4* pa4 = reinterpret_cast<const float4*>(prow_slot + (tk.x & 0xfffu));
-                const float4* pb4 = reinterpret_cast<const float4*>(prow_slot + (tk.y & 0xfffu));
+            const int2 be = reinterpret_cast<const int2*>(s_tbeg)[grp];      // this group's tasks: [be.x, be.y)
+            f2 acc_a = pk(0.f, 0.f), acc_b = pk(0.f, 0.f);
+            auto load_task = [&](uint32_t word, int t, ulonglong2 (&x)[4], float4 (&w)[4]) {
+                const ulonglong2* px = reinterpret_cast<const ulonglong2*>(prow_slot + (word & 0xfffu));
                 const float4* ww = s_wts4 + 4 * t;
-                float4 a[4], b[4], wa[4], wb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = pa4[i]; wa[i] = ww[i]; }
+                for (int i = 0; i < 4; ++i) { x[i] = px[i]; w[i] = ww[i]; }
+            };
+            auto run_task = [&](uint32_t word, const ulonglong2 (&x)[4], const float4 (&w)[4]) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { b[i] = pb4[i]; wb[i] = ww[4 + i]; }
+                for (int i = 0; i < 4; ++i) {
+                    acc_a = fma2(x[i].x, bc(w[i].x), acc_a);
+                    acc_b = fma2(x[i].x, bc(w[i].y), acc_b);
+                    acc_a = fma2(x[i].y, bc(w[i].z), acc_a);
+                    acc_b = fma2(x[i].y, bc(w[i].w), acc_b);
+                }
+                if (word & 0x80000000u) {
+                    *part((word >> 12) & 0x1ffu) = acc_a;
+                    *part((word >> 21) & 0x1ffu) = acc_b;
+                    acc_a = acc_b = pk(0.f, 0.f);
+                }
+            };
+            int t = be.x;
+            uint2 tk = make_uint2(0u, 0u);
+            if (t < be.y) tk.x = s_tasks[t];
+            if (t + 1 < be.y) tk.y = s_tasks[t + 1];
+            for (; t + 1 < be.y; t += 2) {
+                ulonglong2 x[4], y[4];
+                float4 wx[4], wy[4];
+                load_task(tk.x, t, x, wx);
+                load_task(tk.y, t + 1, y, wy);
                 const uint2 cur = tk;
-                if (t + 2 < t_end) tk = *reinterpret_cast<const uint2*>(s_tasks + t + 2);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc0 = __fmaf_rn(a[i].x, wa[i].x, acc0);
-                    acc1 = __fmaf_rn(a[i].y, wa[i].y, acc1);
-                    acc2 = __fmaf_rn(a[i].z, wa[i].z, acc2);
-                    acc3 = __fmaf_rn(a[i].w, wa[i].w, acc3);
-                }
-                if (cur.x & 0x80000000u) {
-                    s_part[((cur.x >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
-                    acc0 = acc1 = acc2 = acc3 = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc0 = __fmaf_rn(b[i].x, wb[i].x, acc0);
-                    acc1 = __fmaf_rn(b[i].y, wb[i].y, acc1);
-                    acc2 = __fmaf_rn(b[i].z, wb[i].z, acc2);
-                    acc3 = __fmaf_rn(b[i].w, wb[i].w, acc3);
-                }
-                if (cur.y & 0x80000000u) {
-                    s_part[((cur.y >> 12) & 0xfffu) * geo::SLOTS + slot] = (acc0 + acc1) + (acc2 + acc3);
-                    acc0 = acc1 = acc2 = acc3 = 0.f;
-                }
+                if (t + 2 < be.y) tk.x = s_tasks[t + 2];
+                if (t + 3 < be.y) tk.y = s_tasks[t + 3];
+                run_task(cur.x, x, wx);
+                run_task(cur.y, y, wy);
+            }
+            if (t < be.y) {                               // odd list: the last task on its own
+                ulonglong2 x[4];
+                float4 wx[4];
+                load_task(tk.x, t, x, wx);
+                run_task(tk.x, x, wx);
             }
         }
         team_sync();
 
         // =========================== log ========================================================
-        const float frame_energy = s_energy[slot];
-        bool silent = false;
-        if constexpr (kEnergyZero) silent = frame_energy < p.zero_energy;
+        const f2 frame_energy = s_energy[slot];
+        bool silent_a = false, silent_b = false;
+        if constexpr (kEnergyZero) {
+            silent_a = lo(frame_energy) < p.zero_energy;
+            silent_b = hi(frame_energy) < p.zero_energy;
+        }
         for (int q = grp; q < p.n_q; q += geo::NGRP) {            // n_q = n_filt (+1: the energy, cepstrum only)
-            float v;
+            f2 v = frame_energy;
             if (q < p.n_filt) {
                 const int2 qs = s_qspec[q];
-                v = s_part[qs.x * geo::SLOTS + slot];
-                for (int j = 1; j < qs.y; ++j) v += s_part[(qs.x + j) * geo::SLOTS + slot];
-            } else {
-                v = frame_energy;
+                v = pk(0.f, 0.f);
+                for (int j = 0; j < qs.y; ++j) v = add2(v, *part(qs.x + j));
             }
-            if (silent) v = 0.f;
-            const float lv = __logf(fmaxf(v, SCF_EPS));          // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
+            // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
+            const float la = __logf(fmaxf(silent_a ? 0.f : lo(v), SCF_EPS));
+            const float lb = __logf(fmaxf(silent_b ? 0.f : hi(v), SCF_EPS));
             if (p.out_kind == SCF_OUT_LOG_BANK) {
-                if (p.n_peers != 0) {
-                    s_logq[slot * p.out_cols + q] = lv;         // staged for the coalesced peer stores below
-                } else if (out_row >= 0) {
-                    p.out[out_row * p.out_cols + q] = lv;
+                if (p.n_peers != 0) {                          // staged for the coalesced peer stores below
+                    s_stage[(2 * slot) * p.out_cols + q] = la;
+                    s_stage[(2 * slot + 1) * p.out_cols + q] = lb;
+                } else if (row_a >= 0) {
+                    p.out[row_a * p.out_cols + q] = la;
+                    if (has_b) p.out[(row_a + 1) * p.out_cols + q] = lb;
                 }
             } else {
-                s_logq[q * geo::SLOTS + slot] = lv;
+                s_logq[q * geo::PPT + slot] = pk(la, lb);
             }
         }
-        // Fused all-gather: the finished rows of this tile sit contiguously in shared memory [slot][col]; every thread
-        // pushes consecutive floats, so each warp writes whole 128-byte segments to every peer's cache over NVLink
-        // (8-byte scattered stores per thread were 3x slower than a separate NCCL all-gather at 8 GPUs).
-        auto push_to_peers = [&](float* stage) {
-            int64_t* s_rows = reinterpret_cast<int64_t*>(s_logq + n_lq * geo::SLOTS);
-            if (grp == 0) s_rows[slot] = out_row;
+        // Fused all-gather: the finished rows of this tile sit contiguously in shared memory [frame slot][col]; every
+        // thread pushes consecutive floats, so each warp writes whole 128-byte segments to every peer's cache over
+        // NVLink (8-byte scattered stores per thread were 3x slower than a separate NCCL all-gather at 8 GPUs).
+        auto push_to_peers = [&]() {
+            int64_t* s_rows = reinterpret_cast<int64_t*>(s_stage + 2 * geo::PPT * p.out_cols);
+            if (grp == 0) {
+                s_rows[2 * slot] = row_a;
+                s_rows[2 * slot + 1] = has_b ? row_a + 1 : -1;
+            }
             team_sync();
-            const int n = geo::SLOTS * p.out_cols;
+            const int n = 2 * geo::PPT * p.out_cols;
             for (int i = tid; i < n; i += kThreads) {
                 const int sl = i / p.out_cols;
                 const int64_t row = s_rows[sl];
                 if (row < 0) continue;
-                const float v = stage[i];
+                const float v = s_stage[i];
                 const int64_t off = (p.peer_row0 + row) * p.out_cols + (i - sl * p.out_cols);
                 for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
             }
         };
         if (p.out_kind == SCF_OUT_LOG_BANK) {
-            if (p.n_peers != 0) {
-                push_to_peers(s_logq);
-                team_sync();                              // s_logq is rewritten by the next tile's log phase
-            }
-            continue;                                     // the next tile's first barrier orders s_part reuse
+            if (p.n_peers != 0) push_to_peers();
+            team_sync();          // the partial-sum rows live in the exchange area: the next tile's pass 1 rewrites them
+            continue;
         }
         team_sync();
 
         // =========================== DCT-II, c0 := log energy ===================================
-        // each thread produces two coefficients of its slot so that the log-band loads are shared
-        for (int c = 2 * grp; c < p.n_out; c += 2 * geo::NGRP) {
-            const bool two = (c + 1) < p.n_out;
-            const float4* d4a = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
-            const float4* d4b = reinterpret_cast<const float4*>(s_dct + (two ? c + 1 : c) * p.n_filt4);
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        // one coefficient of both frames per thread (packed); threads of a quarter warp share the DCT row
+        for (int c = grp; c < p.n_out; c += geo::NGRP) {
+            const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
+            f2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);
             for (int m = 0; m < p.n_filt4; m += 4) {
                 // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
-                const float l0 = s_logq[(m + 0) * geo::SLOTS + slot], l1 = s_logq[(m + 1) * geo::SLOTS + slot];
-                const float l2 = s_logq[(m + 2) * geo::SLOTS + slot], l3 = s_logq[(m + 3) * geo::SLOTS + slot];
-                const float4 da = kDctInL1 ? __ldg(d4a + (m >> 2)) : d4a[m >> 2];
-                const float4 db = kDctInL1 ? __ldg(d4b + (m >> 2)) : d4b[m >> 2];
-                a0 = __fmaf_rn(l0, da.x, a0); a1 = __fmaf_rn(l1, da.y, a1);
-                a0 = __fmaf_rn(l2, da.z, a0); a1 = __fmaf_rn(l3, da.w, a1);
-                b0 = __fmaf_rn(l0, db.x, b0); b1 = __fmaf_rn(l1, db.y, b1);
-                b0 = __fmaf_rn(l2, db.z, b0); b1 = __fmaf_rn(l3, db.w, b1);
+                const f2 l0 = s_logq[(m + 0) * geo::PPT + slot], l1 = s_logq[(m + 1) * geo::PPT + slot];
+                const f2 l2 = s_logq[(m + 2) * geo::PPT + slot], l3 = s_logq[(m + 3) * geo::PPT + slot];
+                const float4 d = kDctInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
+                a0 = fma2(l0, bc(d.x), a0);
+                a1 = fma2(l1, bc(d.y), a1);
+                a0 = fma2(l2, bc(d.z), a0);
+                a1 = fma2(l3, bc(d.w), a1);
             }
-            float va = a0 + a1;
-            const float vb = b0 + b1;
-            if (c == 0) va = s_logq[p.n_filt * geo::SLOTS + slot];
+            f2 v = add2(a0, a1);
+            if (c == 0) v = s_logq[p.n_filt * geo::PPT + slot];
             if (p.n_peers != 0) {
-                float* o = s_part + slot * p.out_cols + c;       // s_part is free during the DCT phase: stage the rows
-                o[0] = va;
-                if (two) o[1] = vb;
-            } else if (out_row >= 0) {
-                float* o = p.out + out_row * p.out_cols + c;
-                o[0] = va;
-                if (two) o[1] = vb;
+                s_stage[(2 * slot) * p.out_cols + c] = lo(v);
+                s_stage[(2 * slot + 1) * p.out_cols + c] = hi(v);
+            } else if (row_a >= 0) {
+                float* o = p.out + row_a * p.out_cols + c;
+                o[0] = lo(v);
+                if (has_b) o[p.out_cols] = hi(v);
             }
         }
-        if (p.n_peers != 0) push_to_peers(s_part);
-        // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no
-        // thread reads after the bank stage; s_part / s_logq are rewritten only behind later barriers.
+        if (p.n_peers != 0) push_to_peers();
+        // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
+        // after the log phase; s_logq / s_energy / s_stage are rewritten only behind later barriers.
     }
 }
 
@@ -667,9 +674,8 @@ template <int R, int TEAMS, bool DENSE>
 static size_t smem_bytes_rt(const KParams& p)
 {
     using geo = Geo<R, DENSE>;
-    const size_t n_lq = (size_t)(p.n_q > p.n_filt4 ? p.n_q : p.n_filt4);
     size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.off_dct : p.table_bytes) +
-               (size_t)TEAMS * ((size_t)p.n_dst + n_lq + 3) * geo::SLOTS * 4 + 16;
+               (size_t)TEAMS * team_smem_floats<geo::PPT>(p) * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -706,7 +712,7 @@ size_t extract_smem_limit(int r, const KParams& p)
 }
 
 int pairs_per_tile(int r) { return kWarps * (32 / r); }
-int bank_groups(int r) { return kThreads / (2 * kWarps * (32 / r)); }
+int bank_groups(int r) { return kThreads / (kWarps * (32 / r)); }
 
 template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
