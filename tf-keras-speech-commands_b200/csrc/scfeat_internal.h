@@ -28,7 +28,7 @@ constexpr int kTaskBins = 8;
 constexpr int pair_row_bins(int r) { return 16 * r + 2; }
 constexpr int pair_row_floats(int r) { return 2 * pair_row_bins(r); }
 // partial-sum rows every kernel layout can hold (they live in the tails of the warps' exchange regions, see Geo)
-constexpr int partial_rows(int r) { return r == 32 ? 496 : r == 16 ? 304 : 184; }
+constexpr int partial_rows(int r) { return r == 32 ? 511 : r == 16 ? 272 : 152; }
 
 // Which partial sums make up output quantity q (filter q, or the frame energy for q == n_filt).
 struct QSpec {

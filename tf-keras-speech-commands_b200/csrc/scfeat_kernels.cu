@@ -29,14 +29,13 @@ namespace scf {
 
 #define SCF_EPS 2.220446049250313e-16f   // np.finfo(float).eps, common/bark_feature.py:77
 
-// SWZ = false: exchange rows are padded by 16 bytes (conflict-free without address arithmetic); 8704 bytes per warp at
-//               n_fft = 1024.
-// SWZ = true : exchange rows are unpadded and XOR-swizzled at float4 granularity; exactly 8192 bytes per warp, which
-//               lets 24 warps share one SM (see TEAMS).
+// Exchange rows (pass 1 -> pass 2 transpose) hold R complex values plus 8 bytes of padding: 64-bit stores of one column
+// by the 32 lanes and 64-bit loads of one row are then conflict-free without any address arithmetic (8448 bytes per warp
+// at n_fft = 1024).
 // After pass 2 the warp's exchange region is free: its head takes the power rows of the warp's pairs (one row per
 // PAIR, the two frames interleaved as (|A[k]|^2, |B[k]|^2) so that the bank phase works on packed values), its tail
 // takes a share of the team's partial-sum rows.
-template <int R, bool SWZ = false>
+template <int R>
 struct Geo {
     static constexpr int NFFT = 32 * R;
     static constexpr int NB = 16 * R;                 // highest bin index (n_fft / 2)
@@ -44,7 +43,7 @@ struct Geo {
     static constexpr int G = 32 / R;                  // frame pairs per warp
     static constexpr int PPT = kWarps * G;            // pairs per tile (one tile = one team's 8 warps) = bank-phase slots
     static constexpr int NGRP = kThreads / PPT;       // bank-phase thread groups
-    static constexpr int XROW = SWZ ? 2 * R : 2 * R + 4;   // floats per exchange row
+    static constexpr int XROW = 2 * R + 2;            // floats per exchange row
     static constexpr int XPAIR = 32 * XROW;
     static constexpr int XWARP = G * XPAIR;           // floats of shared memory owned by one warp
     static constexpr int PROW2 = pair_row_floats(R);  // floats per pair row ( = 4 mod 32 -> conflict-free float4 columns)
@@ -53,8 +52,8 @@ struct Geo {
     static constexpr int DROWS = (XWARP - P_FREE) / DROW;   // partial-sum rows per warp region
     static constexpr int NLOAD = R + R / 2;           // fast path: strided samples per lane covering both frames
     static_assert(P_FREE % 4 == 0 && P_FREE <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(XWARP % 32 == 0, "warp regions must start on bank 0");
     static_assert(kWarps * DROWS >= partial_rows(R), "partial-sum rows promised to the host must fit");
-    static_assert(!SWZ || R == 32, "the swizzled layout is written for n_fft = 1024");
 };
 
 // shared-memory floats per team outside the exchange area (see the carve-up in the kernel)
@@ -62,7 +61,7 @@ template <int PPT>
 __host__ __device__ inline int team_smem_floats(const KParams& p)
 {
     const int n_lq = p.n_q > p.n_filt4 ? p.n_q : p.n_filt4;
-    return 2 * PPT * (n_lq + 1) + (p.n_peers != 0 ? 2 * PPT * (p.out_cols + 2) : 0);
+    return 2 * PPT * (n_lq + 2) + (p.n_peers != 0 ? 2 * PPT * (p.out_cols + 2) : 0);
 }
 
 __device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
@@ -184,21 +183,20 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
     return (t + ((n - t) >> 1)) >> shift;
 }
 
-// TEAMS = 1, DENSE = false ("classic"): a CTA is one team of 8 warps; 2 CTAs per SM, 128 registers per thread, padded
-//            exchange rows, every table in shared memory, next tile's samples prefetched into registers.
-// DENSE = true: 80 registers per thread (the packed FFT fits), XOR-swizzled 8 KB exchange region per warp, bank
-//            weights and DCT matrix read through L1 instead of shared memory -> 24 warps per SM, which is what hides the
-//            FFMA2 / LDS latencies:
-//   TEAMS = 1: 3 CTAs of one team per SM -- small jobs (CTAs of the next launch backfill through PDL);
+// TEAMS = 1, DENSE = false ("classic"): a CTA is one team of 8 warps; 2 CTAs per SM, 128 registers per thread, every
+//            table in shared memory, next tile's samples prefetched into registers.
+// DENSE = true: 80 registers per thread (the packed FFT fits) -> 24 warps per SM, which is what hides the FFMA2 / LDS
+//            latencies:
+//   TEAMS = 1: 3 CTAs of one team per SM -- small jobs (CTAs of the next launch backfill through PDL); the bank
+//              weights and the DCT matrix are read through L1 instead of shared memory to fit three CTAs;
 //   TEAMS = 3: one 768-thread CTA of three independent teams that share one table copy and synchronise through their
 //              own named barriers -- large jobs.
 template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
 __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 : kCtasPerSm))
     extract_kernel(const KParams p, const uint32_t n_tiles)
 {
-    static_assert(TEAMS == 1 || DENSE, "multi-team CTAs need the dense layout");
-    constexpr bool SWZ = DENSE;
-    using geo = Geo<R, SWZ>;
+    static_assert(TEAMS == 1 || DENSE, "multi-team CTAs need the dense register budget");
+    using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
 
     const int tid = threadIdx.x % kThreads;          // thread within its team
@@ -209,23 +207,24 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     // ---- shared memory carve-up (must match extract_smem_bytes; the table part mirrors the plan's blob) ----
     float* s_xch = smem + team * (kWarps * geo::XWARP);
     unsigned char* s_tab = reinterpret_cast<unsigned char*>(smem + TEAMS * kWarps * geo::XWARP);
-    // what is staged in shared memory: everything, except that the 3-CTAs-per-SM variant leaves the DCT matrix in
-    // global memory (read through L1 in the short DCT phase) -- that is what makes its 75 KB budget
-    constexpr bool kDctInL1 = DENSE && TEAMS == 1;
-    const int staged_bytes = kDctInL1 ? p.off_dct : p.table_bytes;
+    // what is staged in shared memory: everything, except that the 3-CTAs-per-SM variant leaves the bank weights and
+    // the DCT matrix in global memory (read through L1) -- that is what makes its 75 KB budget
+    constexpr bool kBankInL1 = DENSE && TEAMS == 1;
+    const int staged_bytes = kBankInL1 ? p.off_wts : p.table_bytes;
+    const unsigned char* big_tab = kBankInL1 ? static_cast<const unsigned char*>(p.tables) : s_tab;
     const float4* s_tw4 = reinterpret_cast<const float4*>(s_tab);
-    const float4* s_wts4 = reinterpret_cast<const float4*>(s_tab + p.off_wts);
-    const float* s_dct = reinterpret_cast<const float*>((kDctInL1 ? static_cast<const unsigned char*>(p.tables) : s_tab) + p.off_dct);
+    const float4* s_wts4 = reinterpret_cast<const float4*>(big_tab + p.off_wts);
+    const float* s_dct = reinterpret_cast<const float*>(big_tab + p.off_dct);
     const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
     const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    // per team: log bands [n_lq][slot] and frame energies [slot] as packed (A, B) pairs; with the fused all-gather
-    // also the finished rows [frame slot][col] and their row ids (int64)
+    // per team: log bands [n_lq][slot] as packed (A, B) pairs, per-slot info (frame energies + output row); with the
+    // fused all-gather also the finished rows [frame slot][col] and their row ids (int64)
     const int team_floats = team_smem_floats<geo::PPT>(p);
     f2* s_logq = reinterpret_cast<f2*>(reinterpret_cast<float*>(s_tab + staged_bytes) + team * team_floats);
-    f2* s_energy = s_logq + n_lq * geo::PPT;                          // written by the FFT stage
-    float* s_stage = reinterpret_cast<float*>(s_energy + geo::PPT);
+    ulonglong2* s_info = reinterpret_cast<ulonglong2*>(s_logq + n_lq * geo::PPT);   // written by the FFT stage
+    float* s_stage = reinterpret_cast<float*>(s_info + geo::PPT);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(s_tab + staged_bytes) + TEAMS * team_floats);
     float* xw = s_xch + warp * geo::XWARP;
     auto team_sync = [&]() {
@@ -271,43 +270,61 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     };
 
     // How exactly-zero frames are recognised (they must produce exactly zero power, see the FFT stage):
-    //  * fast int16 path with a bank: from the frame energy in the epilogue -- a non-zero int16 frame has raw
-    //    energy >= 0.5 while its partner can leak at most ~2e-3 into it, so energy < 0.25 means "all zero";
-    //  * everything else (float input, generic loader, power output): bitwise OR of the samples + warp vote.
+    //  * fast int16 path: from the frame energy in the epilogue -- a non-zero int16 frame has raw energy >= 0.5
+    //    while its partner can leak at most ~2e-3 into it, so energy < 0.25 means "all zero";
+    //  * everything else (float input, generic loader): bitwise OR of the samples + warp vote.
     constexpr bool kEnergyZero = FAST && sizeof(InT) == 2;
-    const bool bit_detect = !kEnergyZero || p.out_kind == SCF_OUT_POWER;
+    constexpr bool bit_detect = !kEnergyZero;
     const InT* __restrict__ in = reinterpret_cast<const InT*>(p.in);
     const uint32_t ppc = (uint32_t)p.pairs_per_clip;
     const uint32_t n_pairs = (uint32_t)p.n_pairs;
     bool tables_ready = false;
 
-    // fast path: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases
-    // of the current tile run (those need few registers), so the FFT stage never waits on HBM
-    // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead)
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;     // (24-warp CTAs have no registers to spare)
+    const uint32_t tile_stride = gridDim.x * TEAMS;
+    const uint32_t tile_first = blockIdx.x * TEAMS + team;
+    // (clip, pair inside the clip) of global pair gp
+    auto pair_pos = [&](uint32_t gp, uint32_t& c_out, uint32_t& q_out) {
+        c_out = fast_div(gp, p.ppc_magic, p.ppc_shift);
+        q_out = gp - c_out * ppc;
+    };
+
+    // fast path (window == n_fft, hop == n_fft/2, full-length clips): frames 2q and 2q+1 share half their samples;
+    // raw[j] = x[n_fft*q + lane + 32 j], j < R + R/2.  Frame B is absent only for the last pair of a clip with an odd
+    // frame count: its upper samples may lie behind the clip and are not touched.
     InT raw[geo::G][geo::NLOAD];
+    auto load_pair = [&](uint32_t clip, uint32_t q, InT (&dst)[geo::NLOAD]) {
+        const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
+        auto ld = [&](const InT* a) { return kBankInL1 ? ld_stream(a) : __ldg(a); };
+        if (__builtin_expect((int)(2 * q + 1) < p.frames_per_clip, 1)) {
+#pragma unroll
+            for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld(src + 32 * j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) dst[j] = ld(src + 32 * j);
+#pragma unroll
+            for (int j = R; j < geo::NLOAD; ++j) dst[j] = (InT)0;
+        }
+    };
+    // classic variant: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases of
+    // the current tile run (those need few registers), so the FFT stage never waits on HBM
+    // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead;
+    //  the 24-warp CTAs have no registers to spare and prefetch into L2 instead)
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;
     auto prefetch = [&](uint32_t tile) {
         if constexpr (kPrefetch) {
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
                 const uint32_t gp = tile * geo::PPT + warp * geo::G + g;
                 if (gp < n_pairs) {
-                    const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                    const uint32_t q = gp - clip * ppc;
-                    const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
-                    const bool b_ok = (int)(2 * q + 1) < p.frames_per_clip;
-#pragma unroll
-                    for (int j = 0; j < R; ++j) raw[g][j] = __ldg(src + 32 * j);
-#pragma unroll
-                    for (int j = R; j < geo::NLOAD; ++j) raw[g][j] = b_ok ? __ldg(src + 32 * j) : (InT)0;
+                    uint32_t clip, q;
+                    pair_pos(gp, clip, q);
+                    load_pair(clip, q, raw[g]);
                 }
             }
         }
     };
-    const uint32_t tile_stride = gridDim.x * TEAMS;
-    const uint32_t tile_first = blockIdx.x * TEAMS + team;
     if (tile_first < n_tiles) prefetch(tile_first);
-    __syncthreads();          // mbarrier init + pads visible (the only CTA-wide barrier)
+    __syncthreads();          // mbarrier init + s_logq pad rows visible (the only CTA-wide barrier)
 
     for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
         const uint32_t pair0 = tile * geo::PPT;
@@ -323,28 +340,24 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             for (int g = 0; g < geo::G; ++g) {
                 const uint32_t gp = pair0 + warp * geo::G + g;
                 if (gp < n_pairs) {
+                    uint32_t clip, q;
+                    pair_pos(gp, clip, q);
                     f2 x[R];                                   // (re, im) = (frame A sample, frame B sample), packed
                     uint32_t nz_a = 0, nz_b = 0;
+                    int n_frames = p.frames_per_clip;          // rows this clip produces
                     if constexpr (FAST) {
-                        if constexpr (!kPrefetch) {            // load now: raw[g][j] = x[n_fft*q + lane + 32 j]
-                            const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                            const uint32_t q = gp - clip * ppc;
-                            const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
-                            const bool b_ok = (int)(2 * q + 1) < p.frames_per_clip;
-#pragma unroll
-                            for (int j = 0; j < R; ++j) raw[g][j] = kDctInL1 ? ld_stream(src + 32 * j) : __ldg(src + 32 * j);
-#pragma unroll
-                            for (int j = R; j < geo::NLOAD; ++j)
-                                raw[g][j] = b_ok ? (kDctInL1 ? ld_stream(src + 32 * j) : __ldg(src + 32 * j)) : (InT)0;
+                        if constexpr (!kPrefetch) {
+                            load_pair(clip, q, raw[g]);
                             // pull the samples this warp needs in its NEXT tile into L2 (one 128-byte line per lane)
-                            const uint32_t gpn = gp + tile_stride * geo::PPT;
-                            if (gpn < n_pairs) {
-                                const uint32_t clipn = fast_div(gpn, p.ppc_magic, p.ppc_shift);
-                                const InT* nsrc = in + (int64_t)clipn * p.clip_stride + (gpn - clipn * ppc) * geo::NFFT;
+                            if (gp + tile_stride * geo::PPT < n_pairs) {
+                                uint32_t clipn, qn;
+                                pair_pos(gp + tile_stride * geo::PPT, clipn, qn);
+                                const InT* nsrc = in + (int64_t)clipn * p.clip_stride + qn * geo::NFFT;
                                 if (lane * 128 < (int)(geo::NLOAD * 32 * sizeof(InT)) + 128)
                                     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(nsrc) + lane * 128));
                             }
                         }
+                        const bool b_absent = (int)(2 * q + 1) >= p.frames_per_clip;      // odd frame count: last pair
                         if (bit_detect) {
                             uint32_t o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
@@ -354,30 +367,24 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                                 o2 |= nz_bits(raw[g][j + R]);
                             }
                             nz_a = o0 | o1;
-                            nz_b = o1 | o2;
+                            nz_b = b_absent ? 0u : (o1 | o2);
                         }
-                        // window == n_fft, hop == n_fft/2, full-length clips: frames 2q and 2q+1 share half their
-                        // samples; raw[g][j] = x[n_fft*q + lane + 32 j], j < R + R/2 (zeros where frame B is absent)
-                        bool b_absent = false;
-                        if (p.frames_per_clip & 1) {
-                            const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                            const uint32_t q = gp - clip * ppc;
-                            b_absent = (int)(2 * q + 1) >= p.frames_per_clip;      // odd frame count: last pair
-                        }
-                        if (b_absent) nz_b = 0;
 #pragma unroll
                         for (int i = 0; i < R; ++i) {
                             const int n1 = scf_bitrev(i, geo::LOG2R);
-                            x[i] = pk(to_f32(raw[g][n1]), b_absent ? 0.f : to_f32(raw[g][n1 + R / 2]));
+                            x[i] = pk(to_f32(raw[g][n1]), to_f32(raw[g][n1 + R / 2]));
+                        }
+                        if (__builtin_expect(b_absent, 0)) {   // frame B does not exist: imaginary parts are zero
+#pragma unroll
+                            for (int i = 0; i < R; ++i) x[i] = pk(lo(x[i]), 0.f);
                         }
                     } else {
-                        const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                        const int q = (int)(gp - clip * ppc);
                         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
+                        n_frames = cg.n_frames;
                         float xr[R], xi[R];
-                        nz_a = load_frame_generic<R, InT>(p, cb, cg, 2 * q, lane, xr);
-                        nz_b = load_frame_generic<R, InT>(p, cb, cg, 2 * q + 1, lane, xi);
+                        nz_a = load_frame_generic<R, InT>(p, cb, cg, 2 * (int)q, lane, xr);
+                        nz_b = load_frame_generic<R, InT>(p, cb, cg, 2 * (int)q + 1, lane, xi);
 #pragma unroll
                         for (int i = 0; i < R; ++i) x[i] = pk(xr[i], xi[i]);
                     }
@@ -385,13 +392,20 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                         if (!__any_sync(0xffffffffu, nz_a != 0)) zero_mask |= 1u << (2 * g);
                         if (!__any_sync(0xffffffffu, nz_b != 0)) zero_mask |= 1u << (2 * g + 1);
                     }
-                    fft_r<R>(x);
-                    ulonglong2* row = reinterpret_cast<ulonglong2*>(xw + g * geo::XPAIR + lane * geo::XROW);
-#pragma unroll
-                    for (int k = 0; k < R; k += 2) {
-                        const int c = k / 2;                       // float4 column; swizzled: c ^ (row & 7)
-                        row[SWZ ? ((c & ~7) | ((c & 7) ^ (lane & 7))) : c] = make_ulonglong2(x[k], x[k + 1]);
+                    // where the pair's rows go (the epilogue threads read this instead of redoing the index math):
+                    // 2 * row of frame A + (frame B present), or -1
+                    if (lane == 0) {
+                        const int f = 2 * (int)q;
+                        long long code = -1;
+                        if (f < n_frames) code = 2 * ((long long)clip * p.frames_per_clip + f) + (f + 1 < n_frames ? 1 : 0);
+                        s_info[warp * geo::G + g].y = (unsigned long long)code;
                     }
+                    fft_r<R>(x);
+                    f2* row = reinterpret_cast<f2*>(xw + g * geo::XPAIR + lane * geo::XROW);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) row[k] = x[k];
+                } else if (lane == 0) {
+                    s_info[warp * geo::G + g].y = ~0ull;
                 }
             }
             __syncwarp();
@@ -420,17 +434,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 #pragma unroll
                 for (int n2 = 0; n2 < 16; ++n2) c[n2 + 16] = fma2(mul_i(c[n2]), bc(hi(wq.y)), mul2(c[n2], bc(lo(wq.y))));
 #pragma unroll
-                for (int n2 = 0; n2 < 32; n2 += 2) {
-                    if constexpr (SWZ) {
-                        const float* base = xw + g2 * geo::XPAIR + 2 * (k1 & 1);
-                        const int c = k1 >> 1;
-                        z[n2] = *reinterpret_cast<const f2*>(base + n2 * geo::XROW + 4 * ((c & ~7) | ((c & 7) ^ (n2 & 7))));
-                        z[n2 + 1] = *reinterpret_cast<const f2*>(base + (n2 + 1) * geo::XROW + 4 * ((c & ~7) | ((c & 7) ^ ((n2 + 1) & 7))));
-                    } else {
-                        z[n2] = *reinterpret_cast<const f2*>(col + n2 * geo::XROW);
-                        z[n2 + 1] = *reinterpret_cast<const f2*>(col + (n2 + 1) * geo::XROW);
-                    }
-                }
+                for (int n2 = 0; n2 < 32; ++n2) z[n2] = *reinterpret_cast<const f2*>(col + n2 * geo::XROW);
                 fft32_p2_tw(z, c, y);
             }
             __syncwarp();    // every lane has read its column: the region may now be reused
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             for (int m = R / 2; m >= 1; m >>= 1) esum = add2(esum, __shfl_xor_sync(0xffffffffu, esum, m));
             if (k1 == 0) {
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
-                s_energy[warp * geo::G + g2] = pk(za ? 0.f : lo(esum) * p.power_scale, zb ? 0.f : hi(esum) * p.power_scale);
+                s_info[warp * geo::G + g2].x = pk(za ? 0.f : lo(esum) * p.power_scale, zb ? 0.f : hi(esum) * p.power_scale);
             }
             if (__builtin_expect(zero_mask != 0, 0)) {                     // rare: exact zeros for silent frames
                 const bool za = (zero_mask >> (2 * g2)) & 1u, zb = (zero_mask >> (2 * g2 + 1)) & 1u;
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 mbar_wait(s_bar, 0);
                 tables_ready = true;
             }
+            if (lane < geo::G) s_info[warp * geo::G + lane].y = ~0ull;          // no pair, no rows
             if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
         }
         if (!deps_done) {         // before this grid's first global store
@@ -492,38 +497,24 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         team_sync();
 
         // =========================== where this thread's pair goes ==============================
-        int64_t row_a = -1;           // output row of frame A; frame B, when present, is the next row
-        bool has_b = false;
-        {
-            const uint32_t gp = pair0 + slot;
-            if (gp < n_pairs) {
-                const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                const int f = 2 * (int)(gp - clip * ppc);
-                int nfr = p.frames_per_clip;
-                if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
-                if (f < nfr) row_a = (int64_t)clip * p.frames_per_clip + f;
-                has_b = f + 1 < nfr;
-            }
-        }
+        const ulonglong2 info = s_info[slot];                    // (frame energies, row code) from the FFT stage
+        const long long row_code = (long long)info.y;
+        const int64_t row_a = row_code >> 1;          // output row of frame A (-1: none); frame B, when present, is the next row
+        const bool has_b = row_code >= 0 && (row_code & 1);
 
         if (p.out_kind == SCF_OUT_POWER) {
             // power_spec(): rows straight out of shared memory, coalesced along the bins;
             // warp w copies frame slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
             for (int s = warp; s < 2 * geo::PPT; s += kWarps) {
-                const uint32_t gp = pair0 + (s >> 1);
-                int64_t row = -1;
-                if (gp < n_pairs) {
-                    const uint32_t clip = fast_div(gp, p.ppc_magic, p.ppc_shift);
-                    const int f = 2 * (int)(gp - clip * ppc) + (s & 1);
-                    int nfr = p.frames_per_clip;
-                    if constexpr (!FAST) nfr = clip_geom(p, clip).n_frames;
-                    if (f < nfr) row = (int64_t)clip * p.frames_per_clip + f;
-                }
-                if (row < 0) continue;
+                const long long code = (long long)s_info[s >> 1].y;
+                if (code < 0 || ((s & 1) && !(code & 1))) continue;
+                const int64_t row = (code >> 1) + (s & 1);
+                const f2 e2 = s_info[s >> 1].x;
+                const bool silent = kEnergyZero && ((s & 1) ? hi(e2) : lo(e2)) < p.zero_energy;
                 const int sw = (s >> 1) / geo::G;
                 const float* src = s_xch + sw * geo::XWARP + 4 * ((geo::G * sw) & 7) + ((s >> 1) % geo::G) * geo::PROW2 + (s & 1);
                 float* dst = p.out + row * p.out_cols;
-                for (int k = lane; k <= geo::NB; k += 32) dst[k] = src[2 * k] * p.power_scale;
+                for (int k = lane; k <= geo::NB; k += 32) dst[k] = silent ? 0.f : src[2 * k] * p.power_scale;
             }
             team_sync();
             continue;
@@ -541,7 +532,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 const ulonglong2* px = reinterpret_cast<const ulonglong2*>(prow_slot + (word & 0xfffu));
                 const float4* ww = s_wts4 + 4 * t;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { x[i] = px[i]; w[i] = ww[i]; }
+                for (int i = 0; i < 4; ++i) { x[i] = px[i]; w[i] = kBankInL1 ? __ldg(ww + i) : ww[i]; }
             };
             auto run_task = [&](uint32_t word, const ulonglong2 (&x)[4], const float4 (&w)[4]) {
 #pragma unroll
@@ -582,7 +573,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         team_sync();
 
         // =========================== log ========================================================
-        const f2 frame_energy = s_energy[slot];
+        const f2 frame_energy = info.x;
         bool silent_a = false, silent_b = false;
         if constexpr (kEnergyZero) {
             silent_a = lo(frame_energy) < p.zero_energy;
@@ -646,7 +637,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
                 const f2 l0 = s_logq[(m + 0) * geo::PPT + slot], l1 = s_logq[(m + 1) * geo::PPT + slot];
                 const f2 l2 = s_logq[(m + 2) * geo::PPT + slot], l3 = s_logq[(m + 3) * geo::PPT + slot];
-                const float4 d = kDctInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
+                const float4 d = kBankInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
                 a0 = fma2(l0, bc(d.x), a0);
                 a1 = fma2(l1, bc(d.y), a1);
                 a0 = fma2(l2, bc(d.z), a0);
@@ -665,7 +656,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         }
         if (p.n_peers != 0) push_to_peers();
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
-        // after the log phase; s_logq / s_energy / s_stage are rewritten only behind later barriers.
+        // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
     }
 }
 
@@ -673,8 +664,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 template <int R, int TEAMS, bool DENSE>
 static size_t smem_bytes_rt(const KParams& p)
 {
-    using geo = Geo<R, DENSE>;
-    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.off_dct : p.table_bytes) +
+    using geo = Geo<R>;
+    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.off_wts : p.table_bytes) +
                (size_t)TEAMS * team_smem_floats<geo::PPT>(p) * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
