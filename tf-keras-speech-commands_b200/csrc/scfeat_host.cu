@@ -194,7 +194,7 @@ struct scf_plan {
     float* d_win = nullptr;
     unsigned char* d_tab_i16 = nullptr;   // bank weights pre-multiplied by the int16 power scale
     unsigned char* d_tab_f32 = nullptr;   // ... by the float-input power scale
-    int table_bytes = 0, table_small_bytes = 0, off_wts = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
+    int table_bytes = 0, table_small_bytes = 0, off_wts = 0, off_tw = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
     int n_tasks = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
     scf::Workspace ws;
 };
@@ -242,7 +242,8 @@ struct TaskList {
     std::vector<int32_t> begin;         // [n_groups][2]: first and one past the last task of the group
     std::vector<double> weights;        // 2 * kTaskBins doubles per task, same order as `words`
     std::vector<QSpec> qspec;           // per filter: its partial-sum rows
-    int n_dst = 0;                      // partial-sum rows in use (row n_dst is the dump row)
+    int n_dst = 0;                      // partial-sum rows in use (including the dump row of unpaired filters)
+    bool overflow = false;              // the rows do not fit into the exchange area
 };
 
 static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins, int radix_r, int n_groups, TaskList& tl)
@@ -297,20 +298,35 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
             done += len;
         }
     }
-    // 4. partial-sum rows, consecutive per filter
+    // 4. partial-sum rows: a filter's rows are consecutive inside one warp region's tail (the log phase walks them with
+    //    a fixed stride); the rows are addressed by their 64-byte-unit offset in the team's exchange area
     tl.qspec.assign(n_filt, QSpec{0, 0});
-    int next = 0;
+    int region = 0, row = 0;
+    tl.n_dst = 0;
+    tl.overflow = false;
+    auto alloc = [&](int count) {
+        if (row + count > drows(radix_r)) { ++region; row = 0; }
+        if (region >= kTeamWarps || count > drows(radix_r)) { tl.overflow = true; region = 0; row = 0; }
+        const int unit = partial_row_unit(radix_r, region, row);
+        row += count;
+        tl.n_dst += count;
+        return unit;
+    };
+    const int unit_step = drow_floats(radix_r) / 16;
     for (int f = 0; f < n_filt; ++f) {
-        tl.qspec[f].dst0 = next;
+        int count = 0;
+        for (const Run& r : runs) count += (r.fa == f) + (r.fb == f);
+        int unit = alloc(count);
+        tl.qspec[f].unit0 = unit;
+        tl.qspec[f].count = count;
         for (Run& r : runs) {
-            if (r.fa == f) r.da = next++;
-            if (r.fb == f) r.db = next++;
+            if (r.fa == f) { r.da = unit; unit += unit_step; }
+            if (r.fb == f) { r.db = unit; unit += unit_step; }
         }
-        tl.qspec[f].count = next - tl.qspec[f].dst0;
     }
-    tl.n_dst = next;
+    const int dump = alloc(1);
     for (Run& r : runs)
-        if (r.fb < 0) r.db = tl.n_dst;                  // dump row
+        if (r.fb < 0) r.db = dump;
     std::vector<size_t> order(runs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return runs[a].k0.size() > runs[b].k0.size(); });
@@ -332,8 +348,8 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
             const Run& r = runs[ri];
             int covered_to = r.seg_lo;                  // bins below this one already have their weight in a task
             for (size_t t = 0; t < r.k0.size(); ++t) {
-                uint32_t word = (uint32_t)(2 * r.k0[t]);
-                if (t + 1 == r.k0.size()) word |= 0x80000000u | ((uint32_t)r.da << 12) | ((uint32_t)r.db << 21);
+                uint32_t word = (uint32_t)(r.k0[t] / 2);
+                if (t + 1 == r.k0.size()) word |= 0x80000000u | ((uint32_t)r.da << 8) | ((uint32_t)r.db << 19);
                 tl.words.push_back(word);
                 for (int i = 0; i < kTaskBins; ++i) {
                     const int k = r.k0[t] + i;
@@ -350,15 +366,15 @@ static void build_tasks(const std::vector<double>& bank, int n_filt, int n_bins,
 
 // The task list evaluated on the host in the order the kernel's bank phase walks it (test hook for the decomposition;
 // pair_row holds (A[k], B[k]) interleaved like the kernel's shared-memory row).
-static void apply_tasks(const TaskList& tl, int n_groups, const std::vector<double>& pair_row, std::vector<double>& sums_a,
-                        std::vector<double>& sums_b)
+static void apply_tasks(const TaskList& tl, int radix_r, int n_groups, const std::vector<double>& pair_row,
+                        std::vector<double>& sums_a, std::vector<double>& sums_b)
 {
-    std::vector<double> pa(tl.n_dst + 1, 0.0), pb(tl.n_dst + 1, 0.0);
+    std::vector<double> pa(2048, 0.0), pb(2048, 0.0);      // indexed by 64-byte unit (11-bit field)
     for (int g = 0; g < n_groups; ++g) {
         double aa = 0, ab = 0, ba = 0, bb = 0;          // (filter a | b) x (frame A | B)
         for (int t = tl.begin[2 * g]; t < tl.begin[2 * g + 1]; ++t) {
             const uint32_t w = tl.words[t];
-            const int off = (int)(w & 0xfffu);
+            const int off = 4 * (int)(w & 0xffu);
             for (int i = 0; i < kTaskBins; ++i) {
                 const double wa = tl.weights[(size_t)t * 2 * kTaskBins + 2 * i];
                 const double wb = tl.weights[(size_t)t * 2 * kTaskBins + 2 * i + 1];
@@ -368,7 +384,7 @@ static void apply_tasks(const TaskList& tl, int n_groups, const std::vector<doub
                 bb += wb * pair_row[off + 2 * i + 1];
             }
             if (w & 0x80000000u) {
-                const int da = (w >> 12) & 0x1ff, db = (w >> 21) & 0x1ff;
+                const int da = (w >> 8) & 0x7ff, db = (w >> 19) & 0x7ff;
                 pa[da] = aa; pb[da] = ab;
                 pa[db] = ba; pb[db] = bb;
                 aa = ab = ba = bb = 0;
@@ -377,10 +393,11 @@ static void apply_tasks(const TaskList& tl, int n_groups, const std::vector<doub
     }
     sums_a.assign(tl.qspec.size(), 0.0);
     sums_b.assign(tl.qspec.size(), 0.0);
+    const int unit_step = drow_floats(radix_r) / 16;
     for (size_t f = 0; f < tl.qspec.size(); ++f)
         for (int j = 0; j < tl.qspec[f].count; ++j) {
-            sums_a[f] += pa[tl.qspec[f].dst0 + j];
-            sums_b[f] += pb[tl.qspec[f].dst0 + j];
+            sums_a[f] += pa[tl.qspec[f].unit0 + j * unit_step];
+            sums_b[f] += pb[tl.qspec[f].unit0 + j * unit_step];
         }
 }
 
@@ -474,7 +491,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         const bool cep = cfg->output == SCF_OUT_CEPSTRUM;
         // (the frame energy -- c0 of the cepstrum -- is summed in the FFT stage, not as a bank row)
         build_tasks(bank, cfg->n_filt, p->n_bins, p->radix_r, bank_groups(p->radix_r), tl);
-        if (tl.n_dst + 1 > partial_rows(p->radix_r)) {
+        if (tl.overflow) {
             free_plan_tables(p);
             delete p;
             return fail(SCF_ERR_INVALID, "filterbank needs more partial sums than the kernel's shared memory holds");
@@ -494,14 +511,15 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     }
     auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t sz_tw = 4 * 32 * sizeof(float4) + 32 * sizeof(float4);    // W^(k1 n2), n2 < 8, then (W^(8 k1), W^(16 k1))
-    // order: the small tables first (always staged in shared memory), then the bank weights and the DCT matrix
-    // (staged too by the classic kernel; read through L1 by the dense variants, which need the space for warps)
-    p->off_tasks = (int)sz_tw;
+    // order: work list, bank weights -- always staged in shared memory -- then the pass-2 twiddles and the DCT matrix
+    // (staged too by the one-CTA-per-SM kernels; read through L1 by the 3-CTA variant, which needs the space for warps)
+    p->off_tasks = 0;
     p->off_tbeg = (int)align16(p->off_tasks + (size_t)p->n_tasks * 4);
     p->off_qspec = (int)align16(p->off_tbeg + tl.begin.size() * 4);
-    p->table_small_bytes = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
-    p->off_wts = p->table_small_bytes;
-    p->off_dct = (int)align16(p->off_wts + (size_t)p->n_tasks * 2 * kTaskBins * 4);
+    p->off_wts = (int)align16(p->off_qspec + tl.qspec.size() * sizeof(QSpec));
+    p->off_tw = (int)align16(p->off_wts + (size_t)p->n_tasks * 2 * kTaskBins * 4);
+    p->table_small_bytes = p->off_tw;
+    p->off_dct = (int)align16(p->off_tw + sz_tw);
     p->table_bytes = (int)align16(p->off_dct + dct_t.size() * 4);
     for (int variant = 0; variant < 2; ++variant) {
         const double ps = variant == 0 ? ps_i16 : ps_f32;
@@ -509,7 +527,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         // pass-2 twiddles: lane L handles column k1 = L % R; W_N^(k1*n2), n2 = 0..31, as float4 pairs
         {
             const int R = p->radix_r, N = cfg->n_fft;
-            float4* tw = reinterpret_cast<float4*>(blob.data());
+            float4* tw = reinterpret_cast<float4*>(blob.data() + p->off_tw);
             for (int jj = 0; jj < 4; ++jj)
                 for (int lane = 0; lane < 32; ++lane) {
                     const int k1 = lane % R;
@@ -575,6 +593,7 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.table_bytes = plan->table_bytes;
     kp.table_small_bytes = plan->table_small_bytes;
     kp.off_wts = plan->off_wts;
+    kp.off_tw = plan->off_tw;
     kp.off_dct = plan->off_dct;
     kp.off_tasks = plan->off_tasks;
     kp.off_tbeg = plan->off_tbeg;
@@ -859,7 +878,8 @@ int scf_bank_apply_tasks(const scf_config* cfg, const double* power_a, const dou
     std::vector<double> row((size_t)pair_row_floats(r), 1e300);
     for (int k = 0; k < n_bins; ++k) { row[2 * k] = power_a[k]; row[2 * k + 1] = power_b[k]; }
     std::vector<double> sa, sb;
-    apply_tasks(tl, n_groups, row, sa, sb);
+    apply_tasks(tl, r, n_groups, row, sa, sb);
+    if (tl.overflow) return fail(SCF_ERR_INVALID, "filterbank needs more partial sums than the kernel's shared memory holds");
     memcpy(sums_a, sa.data(), sa.size() * sizeof(double));
     memcpy(sums_b, sb.data(), sb.size() * sizeof(double));
     if (stats4) {

@@ -19,20 +19,28 @@ constexpr int kMaxPeers = 8;
 // bins (first bin even -> 16-byte aligned) applied to TWO filters at once, so every power value is read once per
 // filter pair and all the arithmetic is packed (FFMA2 on the (A, B) pair with a broadcast weight).
 // Task word:
-//   bits  0..11  float offset of the first bin inside the pair row ( = 2 * first bin, multiple of 4)
-//   bits 12..20  partial-sum row of the first filter      } only read when bit 31 is set
-//   bits 21..29  partial-sum row of the second filter     }
+//   bits  0..7   first bin / 2 ( = 16-byte offset of the task inside the pair row)
+//   bits  8..18  partial-sum row of the first filter      } only read when bit 31 is set; given as the row's
+//   bits 19..29  partial-sum row of the second filter     } offset inside the team's exchange area, in 64-byte units
 //   bit  31      last task of its run: store the two accumulated sums
 // The 16 weights of task t sit at float4 index 4*t of the weight table, as (a[k], b[k], a[k+1], b[k+1]) per float4.
 constexpr int kTaskBins = 8;
 constexpr int pair_row_bins(int r) { return 16 * r + 2; }
 constexpr int pair_row_floats(int r) { return 2 * pair_row_bins(r); }
-// partial-sum rows every kernel layout can hold (they live in the tails of the warps' exchange regions, see Geo)
-constexpr int partial_rows(int r) { return r == 32 ? 511 : r == 16 ? 272 : 152; }
+// Exchange-area geometry shared by the kernels (Geo<R>) and the host-side task builder.  A warp's region holds
+// 32 / r pairs: exchange rows of r complex values + 8 bytes of padding; after pass 2 its head takes the pairs' power
+// rows and its tail `drows` partial-sum rows of `drow` floats (one packed (A, B) value per pair slot of the team).
+constexpr int kTeamWarps = 8;
+constexpr int xwarp_floats(int r) { return (32 / r) * 32 * (2 * r + 2); }
+constexpr int p_free_floats(int r) { return ((32 / r) * pair_row_floats(r) + 28 + 15) / 16 * 16; }
+constexpr int drow_floats(int r) { return 2 * kTeamWarps * (32 / r); }
+constexpr int drows(int r) { return (xwarp_floats(r) - p_free_floats(r)) / drow_floats(r); }
+// 64-byte-unit offset of partial-sum row `i` of warp region `w`
+constexpr int partial_row_unit(int r, int w, int i) { return (w * xwarp_floats(r) + p_free_floats(r) + i * drow_floats(r)) / 16; }
 
-// Which partial sums make up output quantity q (filter q, or the frame energy for q == n_filt).
+// Which partial sums make up filter q: `count` consecutive rows starting at 64-byte unit `unit0`.
 struct QSpec {
-    int32_t dst0;
+    int32_t unit0;
     int32_t count;
 };
 
@@ -60,15 +68,15 @@ struct KParams {
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
     float zero_energy;           // int16 input: frame energies below this mean "every sample was zero"
     // tables: one device blob, copied verbatim into shared memory by a single TMA bulk copy
-    //   [twiddles float4[4][32] + float4[32]] [tasks u32[n_tasks]] [task ranges int2[n_groups]] [qspec int2[n_filt]]
-    //   [weights float4[4*n_tasks]] [dct float[n_out][n_filt4]]                 (every section 16-byte aligned)
+    //   [tasks u32[n_tasks]] [task ranges int2[n_groups]] [qspec int2[n_filt]] [weights float4[4*n_tasks]]
+    //   [twiddles float4[4][32] + float4[32]] [dct float[n_out][n_filt4]]           (every section 16-byte aligned)
     const void* tables;
     int32_t table_bytes;         // whole blob
-    int32_t table_small_bytes;   // leading part without bank weights / DCT (what the dense kernels stage)
-    int32_t off_wts, off_dct, off_tasks, off_tbeg, off_qspec;
+    int32_t table_small_bytes;   // leading part without twiddles / DCT (what the 3-CTA-per-SM kernels stage)
+    int32_t off_wts, off_tw, off_dct, off_tasks, off_tbeg, off_qspec;
     int32_t n_tasks;
     int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)
-    int32_t n_dst;               // number of partial-sum rows (row n_dst is a dump row for unpaired filters)
+    int32_t n_dst;               // number of partial-sum rows in use (informational)
     int32_t n_filt;
     int32_t n_filt4;             // n_filt rounded up to a multiple of 4
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)

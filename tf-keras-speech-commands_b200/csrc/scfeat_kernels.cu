@@ -45,15 +45,13 @@ struct Geo {
     static constexpr int NGRP = kThreads / PPT;       // bank-phase thread groups
     static constexpr int XROW = 2 * R + 2;            // floats per exchange row
     static constexpr int XPAIR = 32 * XROW;
-    static constexpr int XWARP = G * XPAIR;           // floats of shared memory owned by one warp
+    static constexpr int XWARP = xwarp_floats(R);     // floats of shared memory owned by one warp
     static constexpr int PROW2 = pair_row_floats(R);  // floats per pair row ( = 4 mod 32 -> conflict-free float4 columns)
-    static constexpr int P_FREE = G * PROW2 + 28;     // first float behind the (skewed) power rows
-    static constexpr int DROW = 2 * PPT;              // floats per partial-sum row: one packed (A, B) value per slot
-    static constexpr int DROWS = (XWARP - P_FREE) / DROW;   // partial-sum rows per warp region
     static constexpr int NLOAD = R + R / 2;           // fast path: strided samples per lane covering both frames
-    static_assert(P_FREE % 4 == 0 && P_FREE <= XWARP, "power rows must fit in the warp's exchange region");
+    static_assert(XWARP == G * XPAIR && kWarps == kTeamWarps, "geometry helpers out of sync");
+    static_assert(G * PROW2 + 28 <= p_free_floats(R) && p_free_floats(R) <= XWARP, "power rows must fit in the warp's exchange region");
     static_assert(XWARP % 32 == 0, "warp regions must start on bank 0");
-    static_assert(kWarps * DROWS >= partial_rows(R), "partial-sum rows promised to the host must fit");
+    static_assert(drow_floats(R) == 2 * PPT, "one packed value per slot");
 };
 
 // shared-memory floats per team outside the exchange area (see the carve-up in the kernel)
@@ -64,23 +62,35 @@ __host__ __device__ inline int team_smem_floats(const KParams& p)
     return 2 * PPT * (n_lq + 2) + (p.n_peers != 0 ? 2 * PPT * (p.out_cols + 2) : 0);
 }
 
-__device__ __forceinline__ float to_f32(int16_t v) { return (float)v; }
+// Samples in registers: int16 PCM is held sign-extended in 32 bits, so that the conversion is the full-rate
+// I2FP.F32.S32 instead of the quarter-rate, long-latency I2F.S16 the compiler picks for a `short`.
+template <typename InT> struct Raw { typedef float type; };
+template <> struct Raw<int16_t> { typedef int32_t type; };
+#ifdef SCF_I2F_XU
+__device__ __forceinline__ float to_f32(int32_t v) { return (float)(int16_t)v; }
+#else
+__device__ __forceinline__ float to_f32(int32_t v) { return (float)v; }
+#endif
 __device__ __forceinline__ float to_f32(float v) { return v; }
-// streaming sample loads that do not allocate in L1 (the dense kernels keep L1 for the bank weights / DCT matrix)
-__device__ __forceinline__ int16_t ld_stream(const int16_t* p)
+// read-only sample loads; `stream` = do not allocate in L1 (the 3-CTA kernels keep L1 for the bank weights / DCT matrix)
+template <bool STREAM>
+__device__ __forceinline__ int32_t ld_sample(const int16_t* p)
 {
-    short v;
-    asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=h"(v) : "l"(p));
+    int32_t v;
+    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm volatile("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float ld_stream(const float* p)
+template <bool STREAM>
+__device__ __forceinline__ float ld_sample(const float* p)
 {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    else asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 // bits that are set iff the sample is not zero (-0.0f counts as zero)
-__device__ __forceinline__ uint32_t nz_bits(int16_t v) { return (uint32_t)(uint16_t)v; }
+__device__ __forceinline__ uint32_t nz_bits(int32_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
 template <int R>
@@ -129,8 +139,8 @@ __device__ __forceinline__ uint32_t load_frame_generic(const KParams& p, const I
         if (valid && n < p.w_eff) {
             const int64_t a = s0 + n;
             if (a >= 0 && a < cg.len) {
-                v = to_f32(__ldg(clip_base + a));
-                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(__ldg(clip_base + a - 1)), v);
+                v = to_f32(ld_sample<false>(clip_base + a));
+                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(ld_sample<false>(clip_base + a - 1)), v);
             }
             if (p.win != nullptr) v *= __ldg(p.win + n);
         }
@@ -199,21 +209,24 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
 
-    const int tid = threadIdx.x % kThreads;          // thread within its team
-    const int team = threadIdx.x / kThreads;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;                       // warp within its team
+    // (the shuffle tells the compiler that warp-level quantities are warp-uniform: they then live in uniform registers
+    //  instead of the 80 vector registers the packed FFT needs for itself)
+    const int warp_in_cta = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int team = warp_in_cta / kWarps;
+    const int warp = warp_in_cta % kWarps;           // warp within its team
+    const int lane = threadIdx.x & 31;
+    const int tid = warp * 32 + lane;                // thread within its team
 
     // ---- shared memory carve-up (must match extract_smem_bytes; the table part mirrors the plan's blob) ----
     float* s_xch = smem + team * (kWarps * geo::XWARP);
     unsigned char* s_tab = reinterpret_cast<unsigned char*>(smem + TEAMS * kWarps * geo::XWARP);
-    // what is staged in shared memory: everything, except that the 3-CTAs-per-SM variant leaves the bank weights and
+    // what is staged in shared memory: everything, except that the 3-CTAs-per-SM variant leaves the pass-2 twiddles and
     // the DCT matrix in global memory (read through L1) -- that is what makes its 75 KB budget
-    constexpr bool kBankInL1 = DENSE && TEAMS == 1;
-    const int staged_bytes = kBankInL1 ? p.off_wts : p.table_bytes;
-    const unsigned char* big_tab = kBankInL1 ? static_cast<const unsigned char*>(p.tables) : s_tab;
-    const float4* s_tw4 = reinterpret_cast<const float4*>(s_tab);
-    const float4* s_wts4 = reinterpret_cast<const float4*>(big_tab + p.off_wts);
+    constexpr bool kTwInL1 = DENSE && TEAMS == 1;
+    const int staged_bytes = kTwInL1 ? p.table_small_bytes : p.table_bytes;
+    const unsigned char* big_tab = kTwInL1 ? static_cast<const unsigned char*>(p.tables) : s_tab;
+    const float4* s_tw4 = reinterpret_cast<const float4*>(big_tab + p.off_tw);
+    const float4* s_wts4 = reinterpret_cast<const float4*>(s_tab + p.off_wts);
     const float* s_dct = reinterpret_cast<const float*>(big_tab + p.off_dct);
     const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
@@ -264,10 +277,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         const int sw = slot / geo::G;                // warp that produced this slot
         prow_slot = s_xch + sw * geo::XWARP + 4 * ((geo::G * sw) & 7) + (slot % geo::G) * geo::PROW2;
     }
-    // partial-sum row d of this team, this thread's slot
-    auto part = [&](int d) -> f2* {
-        return reinterpret_cast<f2*>(s_xch + (d & 7) * geo::XWARP + geo::P_FREE + (d >> 3) * geo::DROW) + slot;
-    };
+    // partial-sum row at 64-byte unit u of this team's exchange area, this thread's slot
+    f2* const part0 = reinterpret_cast<f2*>(s_xch) + slot;
+    auto part = [&](uint32_t u) -> f2* { return part0 + 8 * u; };
 
     // How exactly-zero frames are recognised (they must produce exactly zero power, see the FFT stage):
     //  * fast int16 path: from the frame energy in the epilogue -- a non-zero int16 frame has raw energy >= 0.5
@@ -291,10 +303,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     // fast path (window == n_fft, hop == n_fft/2, full-length clips): frames 2q and 2q+1 share half their samples;
     // raw[j] = x[n_fft*q + lane + 32 j], j < R + R/2.  Frame B is absent only for the last pair of a clip with an odd
     // frame count: its upper samples may lie behind the clip and are not touched.
-    InT raw[geo::G][geo::NLOAD];
-    auto load_pair = [&](uint32_t clip, uint32_t q, InT (&dst)[geo::NLOAD]) {
+    typedef typename Raw<InT>::type RawT;
+    RawT raw[geo::G][geo::NLOAD];
+    auto load_pair = [&](uint32_t clip, uint32_t q, RawT (&dst)[geo::NLOAD]) {
         const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
-        auto ld = [&](const InT* a) { return kBankInL1 ? ld_stream(a) : __ldg(a); };
+        auto ld = [&](const InT* a) { return ld_sample<kTwInL1>(a); };
         if (__builtin_expect((int)(2 * q + 1) < p.frames_per_clip, 1)) {
 #pragma unroll
             for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld(src + 32 * j);
@@ -302,7 +315,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 #pragma unroll
             for (int j = 0; j < R; ++j) dst[j] = ld(src + 32 * j);
 #pragma unroll
-            for (int j = R; j < geo::NLOAD; ++j) dst[j] = (InT)0;
+            for (int j = R; j < geo::NLOAD; ++j) dst[j] = (RawT)0;
         }
     };
     // classic variant: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases of
@@ -422,10 +435,14 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 f2 z[32], c[32];
                 // twiddles W^(k1 n2): n2 < 8 come from the table, the rest is derived with packed complex multiplies by
                 // W^(8 k1) and W^(16 k1) -- arithmetic is cheap here, shared-memory wavefronts are not
-                const ulonglong2 wq = reinterpret_cast<const ulonglong2*>(s_tw4 + 4 * 32)[lane];     // (W^(8 k1), W^(16 k1))
+                auto ld_tw = [&](int i) {
+                    const float4 t = kTwInL1 ? __ldg(s_tw4 + i) : s_tw4[i];
+                    return make_ulonglong2(pk(t.x, t.y), pk(t.z, t.w));
+                };
+                const ulonglong2 wq = ld_tw(4 * 32 + lane);                          // (W^(8 k1), W^(16 k1))
 #pragma unroll
                 for (int n2 = 0; n2 < 8; n2 += 2) {
-                    const ulonglong2 t = reinterpret_cast<const ulonglong2*>(s_tw4)[(n2 / 2) * 32 + lane];
+                    const ulonglong2 t = ld_tw((n2 / 2) * 32 + lane);
                     c[n2] = t.x;
                     c[n2 + 1] = t.y;
                 }
@@ -529,10 +546,10 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             const int2 be = reinterpret_cast<const int2*>(s_tbeg)[grp];      // this group's tasks: [be.x, be.y)
             f2 acc_a = pk(0.f, 0.f), acc_b = pk(0.f, 0.f);
             auto load_task = [&](uint32_t word, int t, ulonglong2 (&x)[4], float4 (&w)[4]) {
-                const ulonglong2* px = reinterpret_cast<const ulonglong2*>(prow_slot + (word & 0xfffu));
+                const ulonglong2* px = reinterpret_cast<const ulonglong2*>(prow_slot) + (word & 0xffu);
                 const float4* ww = s_wts4 + 4 * t;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { x[i] = px[i]; w[i] = kBankInL1 ? __ldg(ww + i) : ww[i]; }
+                for (int i = 0; i < 4; ++i) { x[i] = px[i]; w[i] = ww[i]; }
             };
             auto run_task = [&](uint32_t word, const ulonglong2 (&x)[4], const float4 (&w)[4]) {
 #pragma unroll
@@ -543,8 +560,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     acc_b = fma2(x[i].y, bc(w[i].w), acc_b);
                 }
                 if (word & 0x80000000u) {
-                    *part((word >> 12) & 0x1ffu) = acc_a;
-                    *part((word >> 21) & 0x1ffu) = acc_b;
+                    *part((word >> 8) & 0x7ffu) = acc_a;
+                    *part((word >> 19) & 0x7ffu) = acc_b;
                     acc_a = acc_b = pk(0.f, 0.f);
                 }
             };
@@ -584,7 +601,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             if (q < p.n_filt) {
                 const int2 qs = s_qspec[q];
                 v = pk(0.f, 0.f);
-                for (int j = 0; j < qs.y; ++j) v = add2(v, *part(qs.x + j));
+                const f2* pr = part(qs.x);
+                for (int j = 0; j < qs.y; ++j) v = add2(v, pr[j * (geo::PPT)]);
             }
             // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
             const float la = __logf(fmaxf(silent_a ? 0.f : lo(v), SCF_EPS));
@@ -637,7 +655,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
                 const f2 l0 = s_logq[(m + 0) * geo::PPT + slot], l1 = s_logq[(m + 1) * geo::PPT + slot];
                 const f2 l2 = s_logq[(m + 2) * geo::PPT + slot], l3 = s_logq[(m + 3) * geo::PPT + slot];
-                const float4 d = kBankInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
+                const float4 d = kTwInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
                 a0 = fma2(l0, bc(d.x), a0);
                 a1 = fma2(l1, bc(d.y), a1);
                 a0 = fma2(l2, bc(d.z), a0);
@@ -665,12 +683,12 @@ template <int R, int TEAMS, bool DENSE>
 static size_t smem_bytes_rt(const KParams& p)
 {
     using geo = Geo<R>;
-    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.off_wts : p.table_bytes) +
+    size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.table_small_bytes : p.table_bytes) +
                (size_t)TEAMS * team_smem_floats<geo::PPT>(p) * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
-constexpr int64_t kTeamsMinPairs = 49152;      // measured crossover vs the 3-CTA variant: ~3300 one-second clips (tools/sweep.py)
+constexpr int64_t kTeamsMinPairs = 30720;      // measured crossover vs the 3-CTA variant: ~2000 one-second clips (tools/sweep.py)
 constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 232448;
 
 // Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM,
