@@ -72,23 +72,14 @@ __device__ __forceinline__ float to_f32(int32_t v) { return (float)(int16_t)v; }
 __device__ __forceinline__ float to_f32(int32_t v) { return (float)v; }
 #endif
 __device__ __forceinline__ float to_f32(float v) { return v; }
-// read-only sample loads; `stream` = do not allocate in L1 (the 3-CTA kernels keep L1 for the bank weights / DCT matrix)
-template <bool STREAM>
+// read-only sample loads
 __device__ __forceinline__ int32_t ld_sample(const int16_t* p)
 {
     int32_t v;
-    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=r"(v) : "l"(p));
-    else asm volatile("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-template <bool STREAM>
-__device__ __forceinline__ float ld_sample(const float* p)
-{
-    float v;
-    if constexpr (STREAM) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    else asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
+__device__ __forceinline__ float ld_sample(const float* p) { return __ldg(p); }
 // bits that are set iff the sample is not zero (-0.0f counts as zero)
 __device__ __forceinline__ uint32_t nz_bits(int32_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
@@ -139,8 +130,8 @@ __device__ __forceinline__ uint32_t load_frame_generic(const KParams& p, const I
         if (valid && n < p.w_eff) {
             const int64_t a = s0 + n;
             if (a >= 0 && a < cg.len) {
-                v = to_f32(ld_sample<false>(clip_base + a));
-                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(ld_sample<false>(clip_base + a - 1)), v);
+                v = to_f32(ld_sample(clip_base + a));
+                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(ld_sample(clip_base + a - 1)), v);
             }
             if (p.win != nullptr) v *= __ldg(p.win + n);
         }
@@ -307,7 +298,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     RawT raw[geo::G][geo::NLOAD];
     auto load_pair = [&](uint32_t clip, uint32_t q, RawT (&dst)[geo::NLOAD]) {
         const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
-        auto ld = [&](const InT* a) { return ld_sample<kTwInL1>(a); };
+        auto ld = [&](const InT* a) { return ld_sample(a); };
         if (__builtin_expect((int)(2 * q + 1) < p.frames_per_clip, 1)) {
 #pragma unroll
             for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld(src + 32 * j);
@@ -688,7 +679,7 @@ static size_t smem_bytes_rt(const KParams& p)
     return (b + 15) & ~(size_t)15;
 }
 
-constexpr int64_t kTeamsMinPairs = 30720;      // measured crossover vs the 3-CTA variant: ~2000 one-second clips (tools/sweep.py)
+constexpr int64_t kTeamsMinPairs = 23040;      // measured crossover vs the 3-CTA variant: ~1500 one-second clips (tools/sweep.py)
 constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 232448;
 
 // Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM,
