@@ -71,6 +71,52 @@ def test_dct_equals_oracle(nf, nc):
     np.testing.assert_allclose(_lib.build_dct(nf, nc), osonopy.dct2_ortho_matrix(nf, nc), rtol=0, atol=1e-15)
 
 
+# The kernel's bank phase does not multiply by the dense bank: the host cuts it into two-filter tasks of 8 bins, runs
+# and partial sums (scfeat_host.cu build_tasks).  scf_bank_apply_tasks walks that work list on the host exactly as the
+# kernel does, so the decomposition is checked against bank @ power without a GPU.
+@pytest.mark.parametrize('kw', [
+    dict(n_fft=1024, n_filt=20, bank=_lib.BANK_MEL_SONOPY),                    # params.json
+    dict(n_fft=1024, n_filt=26, bank=_lib.BANK_BARK_REF),                      # config 5 (bfcc)
+    dict(n_fft=1024, n_filt=24, bank=_lib.BANK_BARK_REF),                      # config 5 (bark_spec)
+    dict(n_fft=512, n_filt=26, bank=_lib.BANK_BARK_REF),                       # bfcc_spec defaults
+    dict(n_fft=512, n_filt=24, bank=_lib.BANK_BARK_REF, bank_scale='ascendant'),
+    dict(n_fft=512, n_filt=20, bank=_lib.BANK_MEL_SONOPY),                     # sonopy defaults
+    dict(n_fft=512, n_filt=40, bank=_lib.BANK_MEL_SONOPY),                     # repeated grid points (correct_grid)
+    dict(n_fft=256, n_filt=13, bank=_lib.BANK_MEL_SONOPY, sample_rate=8000),
+    dict(n_fft=1024, n_filt=64, bank=_lib.BANK_MEL_SONOPY),
+    dict(n_fft=1024, n_filt=64, bank=_lib.BANK_BARK_REF),
+])
+def test_bank_task_list_equals_dense_bank(kw):
+    bank = _lib.build_bank(**kw)
+    rng = np.random.default_rng(11)
+    n_bins = bank.shape[1]
+    pa = rng.random(n_bins) * 10.0 ** rng.uniform(-8, 4, n_bins)               # wide dynamic range
+    pb = rng.random(n_bins)
+    sa, sb, st = _lib.bank_apply_tasks(pa, pb, **kw)
+    np.testing.assert_allclose(sa, bank @ pa, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(sb, bank @ pb, rtol=1e-12, atol=1e-300)
+    assert st['groups'] == 256 // (8 * (1024 // kw['n_fft']))
+    # every thread group gets about the same number of tasks (the bank phase is as long as the longest list)
+    assert st['longest_group'] <= -(-st['tasks'] // st['groups']) + 2
+
+
+def test_bank_task_list_custom_bank_with_holes_and_empty_filter():
+    rng = np.random.default_rng(5)
+    bank = rng.random((7, 513)) * (rng.random((7, 513)) < 0.3)                 # non-contiguous supports
+    bank[3] = 0.0                                                               # a filter without any weight
+    pa, pb = rng.random(513), rng.random(513)
+    sa, sb, _ = _lib.bank_apply_tasks(pa, pb, n_fft=1024, n_filt=7, bank=_lib.BANK_CUSTOM, custom_bank=bank)
+    np.testing.assert_allclose(sa, bank @ pa, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(sb, bank @ pb, rtol=1e-12, atol=1e-14)
+    assert sa[3] == 0.0 and sb[3] == 0.0
+
+
+def test_bank_too_dense_for_shared_memory_is_rejected():
+    # 64 Bark filters on 129 bins need more partial-sum rows than the n_fft = 256 kernel keeps in shared memory
+    with pytest.raises(_lib.ScfError, match='partial sums'):
+        _lib.bank_apply_tasks(np.ones(129), np.ones(129), n_fft=256, n_filt=64, bank=_lib.BANK_BARK_REF)
+
+
 def test_bark_scale_helpers_match_oracle():
     f = np.array([0.0, 100.0, 1000.0, 7999.0])
     np.testing.assert_array_equal(scfeat.bark_feature.hz2bark(f), obark.hz2bark(f))
