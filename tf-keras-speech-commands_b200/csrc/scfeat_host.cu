@@ -201,10 +201,15 @@ struct scf_plan {
 
 struct scf_stream {
     const scf_plan* plan = nullptr;
-    scf::StreamState s{};
+    // double-buffered state: a push reads set `cur` and writes the other one (scfeat_internal.h StreamStep)
+    int16_t* carry[2] = {nullptr, nullptr};     // [n_streams][carry_cap]
+    int32_t* carry_len[2] = {nullptr, nullptr}; // [n_streams]
+    float* ring[2] = {nullptr, nullptr};        // [n_streams][ring_rows][cols]
+    int32_t* n_new = nullptr;                   // [n_streams]
+    int cur = 0;
+    int32_t n_streams = 0, carry_cap = 0, ring_rows = 0, cols = 0;
     int max_chunk = 0;
     int16_t* d_chunk_stage = nullptr;     // for the host-buffer push
-    float* d_ring_stage = nullptr;
 };
 
 namespace scf {
@@ -614,7 +619,8 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
 
 static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out,
-                          float* const* peers, int world, int rank, void* cuda_stream, int64_t clips_per_rank = 0)
+                          float* const* peers, int world, int rank, void* cuda_stream, int64_t clips_per_rank = 0,
+                          const StreamStep* stream_step = nullptr)
 {
     if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
     KParams kp;
@@ -622,6 +628,12 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
     bool fast;
     int rc = fill_params(plan, is_f32, d_in, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, kp, n_tiles, fast);
     if (rc) return rc;
+    if (stream_step) {
+        kp.stream_on = 1;
+        kp.stream = *stream_step;
+        fast = false;             // the generic loader reads concat(carry, chunk)
+    }
+    kp.fast_path = fast ? 1 : 0;
     if (peers) {
         if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(SCF_ERR_INVALID, "bad world/rank");
         if (plan->cfg.output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "fused gather does not support power output");
@@ -1124,21 +1136,19 @@ int scf_stream_create(const scf_plan* plan, int32_t n_streams, int32_t ring_rows
     if (!s) return fail(SCF_ERR_ALLOC, "out of host memory");
     s->plan = plan;
     s->max_chunk = max_chunk;
-    StreamState& st = s->s;
-    st.n_streams = n_streams;
-    st.ring_rows = ring_rows;
-    st.cols = plan->out_cols;
+    s->n_streams = n_streams;
+    s->ring_rows = ring_rows;
+    s->cols = plan->out_cols;
     // carry < window before a push (listen.py:106 leaves len - k*hop < window), so window-1+max_chunk bounds it
-    st.carry_cap = ((plan->cfg.window - 1 + max_chunk) + 7) & ~7;
-    st.max_new = (int32_t)std::max<int64_t>(1, scf_num_frames(st.carry_cap, plan->cfg.window, plan->cfg.hop));
-    cudaError_t e;
-    if ((e = cudaMalloc((void**)&st.carry, (size_t)n_streams * st.carry_cap * 2)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&st.carry_len, (size_t)n_streams * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&st.ring, (size_t)n_streams * ring_rows * st.cols * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&st.fresh, (size_t)n_streams * st.max_new * st.cols * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&st.n_new, (size_t)n_streams * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&s->d_chunk_stage, (size_t)n_streams * max_chunk * 2)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&s->d_ring_stage, (size_t)n_streams * ring_rows * st.cols * 4)) != cudaSuccess) {
+    s->carry_cap = ((plan->cfg.window - 1 + max_chunk) + 7) & ~7;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        if ((e = cudaMalloc((void**)&s->carry[i], (size_t)n_streams * s->carry_cap * 2)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void**)&s->carry_len[i], (size_t)n_streams * 4)) != cudaSuccess) break;
+        e = cudaMalloc((void**)&s->ring[i], (size_t)n_streams * ring_rows * s->cols * 4);
+    }
+    if (e != cudaSuccess || (e = cudaMalloc((void**)&s->n_new, (size_t)n_streams * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&s->d_chunk_stage, (size_t)n_streams * max_chunk * 2)) != cudaSuccess) {
         scf_stream_destroy(s);
         return fail(SCF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
@@ -1153,8 +1163,9 @@ void scf_stream_destroy(scf_stream* s)
 {
     if (!s) return;
     DeviceGuard guard(s->plan->device);
-    cudaFree(s->s.carry); cudaFree(s->s.carry_len); cudaFree(s->s.ring); cudaFree(s->s.fresh); cudaFree(s->s.n_new);
-    cudaFree(s->d_chunk_stage); cudaFree(s->d_ring_stage);
+    for (int i = 0; i < 2; ++i) { cudaFree(s->carry[i]); cudaFree(s->carry_len[i]); cudaFree(s->ring[i]); }
+    cudaFree(s->n_new);
+    cudaFree(s->d_chunk_stage);
     delete s;
 }
 
@@ -1163,11 +1174,10 @@ int scf_stream_reset(scf_stream* s, void* cuda_stream)
     if (!s) return fail(SCF_ERR_INVALID, "stream is NULL");
     DeviceGuard guard(s->plan->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const StreamState& x = s->s;
-    SCF_CUDA(cudaMemsetAsync(x.carry, 0, (size_t)x.n_streams * x.carry_cap * 2, st));
-    SCF_CUDA(cudaMemsetAsync(x.carry_len, 0, (size_t)x.n_streams * 4, st));
-    SCF_CUDA(cudaMemsetAsync(x.ring, 0, (size_t)x.n_streams * x.ring_rows * x.cols * 4, st));
-    SCF_CUDA(cudaMemsetAsync(x.n_new, 0, (size_t)x.n_streams * 4, st));
+    // only the set the next push reads has to be cleared: window_audio = [], mfccs = zeros (listen.py:91-92)
+    SCF_CUDA(cudaMemsetAsync(s->carry_len[s->cur], 0, (size_t)s->n_streams * 4, st));
+    SCF_CUDA(cudaMemsetAsync(s->ring[s->cur], 0, (size_t)s->n_streams * s->ring_rows * s->cols * 4, st));
+    SCF_CUDA(cudaMemsetAsync(s->n_new, 0, (size_t)s->n_streams * 4, st));
     return SCF_OK;
 }
 
@@ -1177,14 +1187,27 @@ int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_le
     if (!s || !d_chunks) return fail(SCF_ERR_INVALID, "NULL argument");
     if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
     const scf_plan* plan = s->plan;
-    DeviceGuard guard(plan->device);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const StreamState& x = s->s;
-    SCF_CUDA(launch_stream_append(x, d_chunks, chunk_len, st));
-    int rc = extract_device(plan, false, x.carry, x.n_streams, x.carry_cap, x.carry_cap, x.carry_len, SCF_PAD_NONE,
-                            x.fresh, nullptr, 0, 0, st);
+    // ONE launch: the extract kernel reads concat(carry, chunk), writes the new ring rows and carries the state over
+    StreamStep ss;
+    memset(&ss, 0, sizeof(ss));
+    const int in = s->cur, out = s->cur ^ 1;
+    ss.chunks = d_chunks;
+    ss.chunk_len = chunk_len;
+    ss.carry_cap = s->carry_cap;
+    ss.carry_in = s->carry[in];
+    ss.carry_out = s->carry[out];
+    ss.len_in = s->carry_len[in];
+    ss.len_out = s->carry_len[out];
+    ss.ring_in = s->ring[in];
+    ss.ring_out = s->ring[out];
+    ss.ring_copy = d_ring_out;
+    ss.n_new = s->n_new;
+    ss.n_new_copy = d_new_rows;
+    ss.ring_rows = s->ring_rows;
+    int rc = extract_device(plan, false, s->carry[in], s->n_streams, s->carry_cap, s->carry_cap, nullptr, SCF_PAD_NONE,
+                            s->ring[out], nullptr, 0, 0, cuda_stream, 0, &ss);
     if (rc) return rc;
-    SCF_CUDA(launch_stream_commit(x, plan->cfg.window, plan->cfg.hop, d_ring_out, d_new_rows, st));
+    s->cur = out;
     return SCF_OK;
 }
 
@@ -1194,15 +1217,14 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
     if (!s || !h_chunks) return fail(SCF_ERR_INVALID, "NULL argument");
     if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
     DeviceGuard guard(s->plan->device);
-    const StreamState& x = s->s;
-    SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)x.n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
-    int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, h_ring_out ? s->d_ring_stage : nullptr, nullptr, nullptr);
+    SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)s->n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
+    int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    if (h_ring_out)
-        SCF_CUDA(cudaMemcpyAsync(h_ring_out, s->d_ring_stage, (size_t)x.n_streams * x.ring_rows * x.cols * 4,
+    if (h_ring_out)         // the new ring is the state buffer the push just wrote
+        SCF_CUDA(cudaMemcpyAsync(h_ring_out, s->ring[s->cur], (size_t)s->n_streams * s->ring_rows * s->cols * 4,
                                  cudaMemcpyDeviceToHost, nullptr));
     if (h_new_rows)
-        SCF_CUDA(cudaMemcpyAsync(h_new_rows, x.n_new, (size_t)x.n_streams * 4, cudaMemcpyDeviceToHost, nullptr));
+        SCF_CUDA(cudaMemcpyAsync(h_new_rows, s->n_new, (size_t)s->n_streams * 4, cudaMemcpyDeviceToHost, nullptr));
     SCF_CUDA(cudaStreamSynchronize(nullptr));
     return SCF_OK;
 }

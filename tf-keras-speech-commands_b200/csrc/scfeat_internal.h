@@ -44,6 +44,27 @@ struct QSpec {
     int32_t count;
 };
 
+// One step of the streaming state machine of Listener.update_vectors (listen.py:96-114), fused into the extract
+// kernel (int16 input, generic loader): "clip" s is stream s, its samples are concat(carry_in[s], chunks[s]) without
+// that buffer ever being written; the kernel's rows are the k newest ring rows, and the team that owns the stream's
+// first pair also writes the surviving ring rows and the new carry.  State is double buffered (in -> out), so no thread
+// ever reads what another one writes in the same launch.
+struct StreamStep {
+    const int16_t* chunks;       // [n_streams][chunk_len]                      (listen.py:101 `chunk`)
+    int32_t chunk_len;
+    int32_t carry_cap;           // elements per carry buffer
+    const int16_t* carry_in;     // [n_streams][carry_cap]                      (`window_audio` before the push)
+    int16_t* carry_out;          //                                             (`window_audio[k*hop:]`, listen.py:106)
+    const int32_t* len_in;       // [n_streams] valid samples of carry_in
+    int32_t* len_out;
+    const float* ring_in;        // [n_streams][ring_rows][cols]                (`mfccs` before the push)
+    float* ring_out;             //                                             (listen.py:107-109)
+    float* ring_copy;            // nullable: the caller's copy of the new ring
+    int32_t* n_new;              // [n_streams] frames emitted by this step
+    int32_t* n_new_copy;         // nullable
+    int32_t ring_rows;
+};
+
 // Everything a launch needs; passed by value (fits the 4 KB parameter space easily).
 struct KParams {
     const void* in;              // int16_t* or float*
@@ -81,6 +102,9 @@ struct KParams {
     int32_t n_filt4;             // n_filt rounded up to a multiple of 4
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)
     uint32_t ppc_magic, ppc_shift;   // fast division by pairs_per_clip
+    int32_t fast_path;           // 1: window == n_fft, hop == n_fft/2, full clips, no window / pre-emphasis (FAST kernels)
+    int32_t stream_on;           // 1: `stream` describes a streaming step (in == stream.carry_in, lengths unused)
+    StreamStep stream;
 };
 
 // scfeat_kernels.cu
@@ -91,18 +115,6 @@ size_t extract_smem_limit(int radix_r, const KParams& p);
 int pairs_per_tile(int radix_r);
 int bank_groups(int radix_r);
 
-// streaming helpers (scfeat_kernels.cu)
-struct StreamState {
-    int16_t* carry;        // [n_streams][carry_cap]
-    int32_t* carry_len;    // [n_streams]
-    float* ring;           // [n_streams][ring_rows][cols]
-    float* fresh;          // [n_streams][max_new][cols]
-    int32_t* n_new;        // [n_streams]
-    int32_t n_streams, carry_cap, ring_rows, cols, max_new;
-};
-cudaError_t launch_stream_append(const StreamState& s, const int16_t* chunks, int chunk_len, cudaStream_t st);
-cudaError_t launch_stream_commit(const StreamState& s, int window, int hop, float* ring_out, int32_t* new_out,
-                                 cudaStream_t st);
 cudaError_t launch_fp32_probe(float* out, int iters, int grid, cudaStream_t st);
 
 void count_launch(int n);

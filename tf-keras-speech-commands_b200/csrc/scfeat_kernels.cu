@@ -102,7 +102,8 @@ __device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
 {
     ClipGeom g;
     int32_t len = p.clip_len;
-    if (p.lengths != nullptr) len = min(max(__ldg(p.lengths + clip), 0), p.clip_len);
+    if (p.stream_on) len = __ldg(p.stream.len_in + clip) + p.stream.chunk_len;      // concat(carry, chunk)
+    else if (p.lengths != nullptr) len = min(max(__ldg(p.lengths + clip), 0), p.clip_len);
     g.len = len;
     if (p.pad_mode == SCF_PAD_FRONT_ZERO) {
         g.pad = p.clip_len - len;
@@ -114,31 +115,55 @@ __device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
     return g;
 }
 
-// Generic loader: any window / hop / per-clip length / pre-emphasis / window function.
+// Generic loader: any window / hop / per-clip length / pre-emphasis / window function; loads the two frames of a pair.
+// Sample a of the clip comes from clip_base[a] for a < split and from tail[a - split] behind it (streaming: carry,
+// then the new chunk).  Branch-free: every lane issues all its loads of BOTH frames back to back (out-of-range
+// positions read clip_base[0], which always exists, and are zeroed afterwards), so the memory latency is paid once
+// per pair, not once per sample.
 template <int R, typename InT>
-__device__ __forceinline__ uint32_t load_frame_generic(const KParams& p, const InT* __restrict__ clip_base,
-                                                       const ClipGeom& cg, int frame, int lane, float (&dst)[R])
+__device__ __forceinline__ void load_pair_generic(const KParams& p, const InT* __restrict__ clip_base,
+                                                  const InT* __restrict__ tail, int split, const ClipGeom& cg, int frame_a,
+                                                  int lane, float (&xa)[R], float (&xb)[R], uint32_t& nz_a, uint32_t& nz_b)
 {
-    uint32_t nz = 0;
-    const bool valid = frame < cg.n_frames;
-    const int64_t s0 = (int64_t)frame * p.hop - cg.pad;     // index of sample n = 0 in the clip's own data
+    typedef typename Raw<InT>::type RawT;
+    auto pos = [&](int i) { return lane + 32 * scf_bitrev(i, Geo<R>::LOG2R); };
+    auto in_range = [&](int frame, int n) {
+        const int a = frame * p.hop - cg.pad + n;         // index in the clip's own data
+        return frame < cg.n_frames && n < p.w_eff && a >= 0 && a < cg.len;
+    };
+    auto addr = [&](int a) { return a < split ? clip_base + a : tail + (a - split); };
+    auto fetch = [&](int frame, int back, RawT (&raw)[R]) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int n = pos(i), a = frame * p.hop - cg.pad + n - back;
+            raw[i] = ld_sample(in_range(frame, n) && a >= 0 ? addr(a) : clip_base);
+        }
+    };
+    RawT ra[R], rb[R];
+    fetch(frame_a, 0, ra);
+    fetch(frame_a + 1, 0, rb);
+#pragma unroll
+    for (int i = 0; i < R; ++i) { xa[i] = to_f32(ra[i]); xb[i] = to_f32(rb[i]); }
+    if (p.preemph != 0.f) {                                   // x[a] - alpha * x[a-1], x[-1] := 0 (mfcc.h:394-403)
+        fetch(frame_a, 1, ra);
+        fetch(frame_a + 1, 1, rb);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int n = pos(i);
+            if (frame_a * p.hop - cg.pad + n >= 1) xa[i] = fmaf(-p.preemph, to_f32(ra[i]), xa[i]);
+            if ((frame_a + 1) * p.hop - cg.pad + n >= 1) xb[i] = fmaf(-p.preemph, to_f32(rb[i]), xb[i]);
+        }
+    }
+    nz_a = nz_b = 0;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const int n1 = scf_bitrev(i, Geo<R>::LOG2R);
-        const int n = lane + 32 * n1;
-        float v = 0.f;
-        if (valid && n < p.w_eff) {
-            const int64_t a = s0 + n;
-            if (a >= 0 && a < cg.len) {
-                v = to_f32(ld_sample(clip_base + a));
-                if (p.preemph != 0.f && a >= 1) v = fmaf(-p.preemph, to_f32(ld_sample(clip_base + a - 1)), v);
-            }
-            if (p.win != nullptr) v *= __ldg(p.win + n);
-        }
-        nz |= nz_bits(v);
-        dst[i] = v;
+        const int n = pos(i);
+        const float w = (p.win != nullptr && n < p.w_eff) ? __ldg(p.win + n) : 1.f;
+        xa[i] = in_range(frame_a, n) ? xa[i] * w : 0.f;
+        xb[i] = in_range(frame_a + 1, n) ? xb[i] * w : 0.f;
+        nz_a |= nz_bits(xa[i]);
+        nz_b |= nz_bits(xb[i]);
     }
-    return nz;
 }
 
 // ---- small PTX helpers: mbarrier + TMA 1-D bulk copy (tables -> shared memory) -----------------------
@@ -386,9 +411,16 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
                         n_frames = cg.n_frames;
+                        const InT* tail = cb;
+                        int split = 0x7fffffff;
+                        if constexpr (sizeof(InT) == 2) {
+                            if (p.stream_on) {
+                                split = cg.len - p.stream.chunk_len;
+                                tail = reinterpret_cast<const InT*>(p.stream.chunks) + (int64_t)clip * p.stream.chunk_len;
+                            }
+                        }
                         float xr[R], xi[R];
-                        nz_a = load_frame_generic<R, InT>(p, cb, cg, 2 * (int)q, lane, xr);
-                        nz_b = load_frame_generic<R, InT>(p, cb, cg, 2 * (int)q + 1, lane, xi);
+                        load_pair_generic<R, InT>(p, cb, tail, split, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
 #pragma unroll
                         for (int i = 0; i < R; ++i) x[i] = pk(xr[i], xi[i]);
                     }
@@ -397,11 +429,20 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                         if (!__any_sync(0xffffffffu, nz_b != 0)) zero_mask |= 1u << (2 * g + 1);
                     }
                     // where the pair's rows go (the epilogue threads read this instead of redoing the index math):
-                    // 2 * row of frame A + (frame B present), or -1
+                    // 4 * (row of frame A + 1) + 2 * (frame A is stored) + (frame B is stored), or -1
                     if (lane == 0) {
                         const int f = 2 * (int)q;
-                        long long code = -1;
-                        if (f < n_frames) code = 2 * ((long long)clip * p.frames_per_clip + f) + (f + 1 < n_frames ? 1 : 0);
+                        long long row = (long long)clip * p.frames_per_clip + f;
+                        bool st_a = f < n_frames, st_b = f + 1 < n_frames;
+                        if constexpr (!FAST) {
+                            if (p.stream_on) {        // the k new frames are the k last ring rows (listen.py:107-109)
+                                const int r = p.stream.ring_rows - n_frames + f;
+                                row = (long long)clip * p.stream.ring_rows + r;
+                                st_a = st_a && r >= 0;
+                                st_b = st_b && r + 1 >= 0;
+                            }
+                        }
+                        const long long code = (st_a || st_b) ? 4 * (row + 1) + (st_a ? 2 : 0) + (st_b ? 1 : 0) : -1;
                         s_info[warp * geo::G + g].y = (unsigned long long)code;
                     }
                     fft_r<R>(x);
@@ -507,16 +548,16 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         // =========================== where this thread's pair goes ==============================
         const ulonglong2 info = s_info[slot];                    // (frame energies, row code) from the FFT stage
         const long long row_code = (long long)info.y;
-        const int64_t row_a = row_code >> 1;          // output row of frame A (-1: none); frame B, when present, is the next row
-        const bool has_b = row_code >= 0 && (row_code & 1);
+        const int64_t row_a = (row_code >> 2) - 1;    // output row of frame A; frame B is the next row
+        const bool has_a = row_code >= 0 && (row_code & 2), has_b = row_code >= 0 && (row_code & 1);
 
         if (p.out_kind == SCF_OUT_POWER) {
             // power_spec(): rows straight out of shared memory, coalesced along the bins;
             // warp w copies frame slots w, w+8, ...; the row index is recomputed per slot (warp-uniform)
             for (int s = warp; s < 2 * geo::PPT; s += kWarps) {
                 const long long code = (long long)s_info[s >> 1].y;
-                if (code < 0 || ((s & 1) && !(code & 1))) continue;
-                const int64_t row = (code >> 1) + (s & 1);
+                if (code < 0 || !(code & ((s & 1) ? 1 : 2))) continue;
+                const int64_t row = (code >> 2) - 1 + (s & 1);
                 const f2 e2 = s_info[s >> 1].x;
                 const bool silent = kEnergyZero && ((s & 1) ? hi(e2) : lo(e2)) < p.zero_energy;
                 const int sw = (s >> 1) / geo::G;
@@ -602,9 +643,15 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 if (p.n_peers != 0) {                          // staged for the coalesced peer stores below
                     s_stage[(2 * slot) * p.out_cols + q] = la;
                     s_stage[(2 * slot + 1) * p.out_cols + q] = lb;
-                } else if (row_a >= 0) {
-                    p.out[row_a * p.out_cols + q] = la;
+                } else {
+                    if (has_a) p.out[row_a * p.out_cols + q] = la;
                     if (has_b) p.out[(row_a + 1) * p.out_cols + q] = lb;
+                    if constexpr (!FAST) {
+                        if (p.stream_on && p.stream.ring_copy != nullptr) {
+                            if (has_a) p.stream.ring_copy[row_a * p.out_cols + q] = la;
+                            if (has_b) p.stream.ring_copy[(row_a + 1) * p.out_cols + q] = lb;
+                        }
+                    }
                 }
             } else {
                 s_logq[q * geo::PPT + slot] = pk(la, lb);
@@ -616,7 +663,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         auto push_to_peers = [&]() {
             int64_t* s_rows = reinterpret_cast<int64_t*>(s_stage + 2 * geo::PPT * p.out_cols);
             if (grp == 0) {
-                s_rows[2 * slot] = row_a;
+                s_rows[2 * slot] = has_a ? row_a : -1;
                 s_rows[2 * slot + 1] = has_b ? row_a + 1 : -1;
             }
             team_sync();
@@ -630,8 +677,65 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
             }
         };
+        // Streaming step: the team that holds a stream's first pair carries its state over -- the surviving ring rows
+        // move up by k (the k new rows were just written by whoever computed them), the carry becomes
+        // concat(carry, chunk)[k * hop:] (listen.py:106-109).  Everything is read from the `in` buffers and written to
+        // the `out` buffers, so the order among teams and launches' threads does not matter.
+        auto stream_update = [&]() {
+            if constexpr (!FAST && sizeof(InT) == 2) {
+                if (!p.stream_on) return;
+                const StreamStep& ss = p.stream;
+                const int cols = p.out_cols;
+                for (int i = warp; i < geo::PPT; i += kWarps) {          // one warp per stream, 8 loads in flight per lane
+                    const uint32_t gp = pair0 + i;
+                    if (gp >= n_pairs) break;
+                    uint32_t clip, q;
+                    pair_pos(gp, clip, q);
+                    if (q != 0) continue;
+                    const int len_old = __ldg(ss.len_in + clip);
+                    const int len = len_old + ss.chunk_len;
+                    const int k = (len >= p.window) ? (len - p.window) / p.hop + 1 : 0;
+                    const int consumed = k * p.hop, keep = len - consumed;
+                    const int16_t* cin = ss.carry_in + (int64_t)clip * ss.carry_cap;
+                    const int16_t* ch = ss.chunks + (int64_t)clip * ss.chunk_len;
+                    int16_t* cout = ss.carry_out + (int64_t)clip * ss.carry_cap;
+                    for (int j0 = lane; j0 < keep; j0 += 32 * 8) {
+                        int16_t v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + 32 * u, a = consumed + j;
+                            v[u] = j < keep ? (a < len_old ? __ldg(cin + a) : __ldg(ch + (a - len_old))) : (int16_t)0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (j0 + 32 * u < keep) cout[j0 + 32 * u] = v[u];
+                    }
+                    const int kk = min(k, ss.ring_rows);
+                    const int n_old = (ss.ring_rows - kk) * cols;
+                    const int64_t r0 = (int64_t)clip * ss.ring_rows * cols;
+                    for (int j0 = lane; j0 < n_old; j0 += 32 * 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = j0 + 32 * u < n_old ? __ldg(ss.ring_in + r0 + kk * cols + j0 + 32 * u) : 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (j0 + 32 * u < n_old) {
+                                ss.ring_out[r0 + j0 + 32 * u] = v[u];
+                                if (ss.ring_copy != nullptr) ss.ring_copy[r0 + j0 + 32 * u] = v[u];
+                            }
+                        }
+                    }
+                    if (lane == 0) {
+                        ss.len_out[clip] = keep;
+                        ss.n_new[clip] = k;
+                        if (ss.n_new_copy != nullptr) ss.n_new_copy[clip] = k;
+                    }
+                }
+            }
+        };
         if (p.out_kind == SCF_OUT_LOG_BANK) {
             if (p.n_peers != 0) push_to_peers();
+            stream_update();
             team_sync();          // the partial-sum rows live in the exchange area: the next tile's pass 1 rewrites them
             continue;
         }
@@ -657,13 +761,21 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             if (p.n_peers != 0) {
                 s_stage[(2 * slot) * p.out_cols + c] = lo(v);
                 s_stage[(2 * slot + 1) * p.out_cols + c] = hi(v);
-            } else if (row_a >= 0) {
+            } else {
                 float* o = p.out + row_a * p.out_cols + c;
-                o[0] = lo(v);
+                if (has_a) o[0] = lo(v);
                 if (has_b) o[p.out_cols] = hi(v);
+                if constexpr (!FAST) {
+                    if (p.stream_on && p.stream.ring_copy != nullptr) {
+                        float* o2 = p.stream.ring_copy + row_a * p.out_cols + c;
+                        if (has_a) o2[0] = lo(v);
+                        if (has_b) o2[p.out_cols] = hi(v);
+                    }
+                }
             }
         }
         if (p.n_peers != 0) push_to_peers();
+        stream_update();
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
         // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
     }
@@ -687,7 +799,7 @@ constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 23244
 int variant_for(int r, const KParams& p)
 {
     static const int forced = [] { const char* e = getenv("SCFEAT_VARIANT"); return e ? atoi(e) : -1; }();
-    if (r != 32 || forced == 0) return 0;
+    if (r != 32 || forced == 0 || !p.fast_path) return 0;     // (the generic loader needs the classic register budget)
     const bool fits3 = smem_bytes_rt<32, 3, true>(p) <= kSmemMaxBlock;
     const bool fits1 = 3 * (smem_bytes_rt<32, 1, true>(p) + kSmemReserve) <= kSmemPerSm;
     if (forced == 3 && fits3) return 3;
@@ -753,12 +865,17 @@ template <int R, int TEAMS, bool DENSE>
 static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
                             size_t smem)
 {
-    if (is_f32) {
-        return fast ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
-                    : launch_one<R, float, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+    if constexpr (DENSE) {        // fast path only (variant_for)
+        return is_f32 ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                      : launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+    } else {
+        if (is_f32) {
+            return fast ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                        : launch_one<R, float, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+        }
+        return fast ? launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                    : launch_one<R, int16_t, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
     }
-    return fast ? launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
-                : launch_one<R, int16_t, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
 }
 
 cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
@@ -775,85 +892,6 @@ cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int6
         case 8: return launch_r<8, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Streaming state machine of Listener.update_vectors (listen.py:96-114) for n_streams listeners.
-//   append : window_audio = concat(window_audio, chunk)                       (listen.py:101)
-//   [extract_kernel over the carry buffers, SCF_PAD_NONE, lengths = carry_len -> `fresh` rows]
-//   commit : k = frames emitted; window_audio = window_audio[k*hop:]          (listen.py:106)
-//            mfccs = concat(mfccs[k:], new_features)                          (listen.py:107-109)
-__global__ void stream_append_kernel(StreamState s, const int16_t* __restrict__ chunks, int chunk_len)
-{
-    const int st = blockIdx.x;
-    const int len = s.carry_len[st];
-    int16_t* dst = s.carry + (int64_t)st * s.carry_cap + len;
-    const int16_t* src = chunks + (int64_t)st * chunk_len;
-    for (int i = threadIdx.x; i < chunk_len; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    if (threadIdx.x == 0) s.carry_len[st] = len + chunk_len;
-}
-
-__global__ void stream_commit_kernel(StreamState s, int window, int hop, float* __restrict__ ring_out,
-                                     int32_t* __restrict__ new_out)
-{
-    extern __shared__ int16_t s_keep[];
-    const int st = blockIdx.x;
-    const int len = s.carry_len[st];
-    int k = (len >= window) ? (len - window) / hop + 1 : 0;
-    const int consumed = k * hop;
-    const int keep = len - consumed;
-    int16_t* carry = s.carry + (int64_t)st * s.carry_cap;
-    // shift the carry down through shared memory (source and destination overlap)
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) s_keep[i] = carry[consumed + i];
-    // ring update: drop the k oldest rows, append the k newest of `fresh`
-    const int rows = s.ring_rows, cols = s.cols;
-    float* ring = s.ring + (int64_t)st * rows * cols;
-    const float* fresh = s.fresh + (int64_t)st * s.max_new * cols;
-    const int kk = min(k, rows);                  // listen.py:107-108 keeps only the newest `rows`
-    const int fresh0 = k - kk;
-    __syncthreads();
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) carry[i] = s_keep[i];
-    if (kk > 0) {
-        const int n_old = (rows - kk) * cols;
-        // move surviving rows up; each element is read before a later iteration could overwrite it only
-        // if processed in order, so go through registers in bounded batches
-        for (int base = 0; base < n_old; base += blockDim.x) {
-            const int i = base + threadIdx.x;
-            float v = 0.f;
-            if (i < n_old) v = ring[i + kk * cols];
-            __syncthreads();
-            if (i < n_old) ring[i] = v;
-            __syncthreads();
-        }
-        for (int i = threadIdx.x; i < kk * cols; i += blockDim.x) ring[n_old + i] = fresh[fresh0 * cols + i];
-    }
-    __syncthreads();
-    if (ring_out != nullptr) {
-        float* o = ring_out + (int64_t)st * rows * cols;
-        for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) o[i] = ring[i];
-    }
-    if (threadIdx.x == 0) {
-        s.carry_len[st] = keep;
-        s.n_new[st] = k;
-        if (new_out != nullptr) new_out[st] = k;
-    }
-}
-
-cudaError_t launch_stream_append(const StreamState& s, const int16_t* chunks, int chunk_len, cudaStream_t st)
-{
-    stream_append_kernel<<<s.n_streams, 128, 0, st>>>(s, chunks, chunk_len);
-    count_launch(1);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_stream_commit(const StreamState& s, int window, int hop, float* ring_out, int32_t* new_out,
-                                 cudaStream_t st)
-{
-    stream_commit_kernel<<<s.n_streams, 128, (size_t)s.carry_cap * sizeof(int16_t), st>>>(s, window, hop, ring_out,
-                                                                                         new_out);
-    count_launch(1);
-    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
