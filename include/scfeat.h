@@ -175,7 +175,9 @@ int scf_stream_reset(scf_stream* s, void* cuda_stream);
 
 /* d_chunks: [n_streams][chunk_len] int16.  After the call (stream-ordered) d_ring_out, if not NULL,
  * holds [n_streams][ring_rows][out_cols] oldest->newest; d_new_rows, if not NULL, the number of frames
- * each stream emitted this step. */
+ * each stream emitted this step.  One kernel launch per push; the object's device state is double buffered
+ * and flipped at enqueue time, so the pushes (and resets) of one scf_stream must be issued in order on ONE
+ * cuda_stream (or be ordered by the caller). */
 int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_len, float* d_ring_out,
                         int32_t* d_new_rows, void* cuda_stream);
 int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chunk_len, float* h_ring_out,

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Throughput vs batch size for the params.json MFCC plan (device-resident int16 input).
-Usage: [SCFEAT_TEAMS=1|3] python tools/sweep.py"""
+Usage: [SCFEAT_VARIANT=0|1|3] python tools/sweep.py   (0 classic, 1 dense 3 CTAs/SM, 3 three-team CTA; default: automatic)"""
 import os
 import sys
 
@@ -29,4 +29,4 @@ for n in (512, 1024, 2048, 4096, 8192, 16384, 65536):
         e0.record(); run(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / reps)
     res.append('%d:%.2fM' % (n, n / best / 1e3))
-print('TEAMS=%s  ' % os.environ.get('SCFEAT_TEAMS', 'auto') + '  '.join(res))
+print('VARIANT=%s  ' % os.environ.get('SCFEAT_VARIANT', 'auto') + '  '.join(res))
