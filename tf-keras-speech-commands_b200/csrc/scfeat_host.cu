@@ -641,6 +641,7 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
         kp.n_peers = world;
         for (int r = 0; r < world; ++r) {
             if (!peers[r]) return fail(SCF_ERR_INVALID, "peer pointer is NULL");
+            if (reinterpret_cast<uintptr_t>(peers[r]) & 15) return fail(SCF_ERR_INVALID, "peer buffers must be 16-byte aligned");
             kp.peer_out[r] = peers[r];
         }
         if (clips_per_rank < n_clips) return fail(SCF_ERR_INVALID, "clips_per_rank must be >= n_local");

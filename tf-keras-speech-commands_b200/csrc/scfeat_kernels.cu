@@ -668,13 +668,25 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             }
             team_sync();
             const int n = 2 * geo::PPT * p.out_cols;
-            for (int i = tid; i < n; i += kThreads) {
-                const int sl = i / p.out_cols;
-                const int64_t row = s_rows[sl];
-                if (row < 0) continue;
-                const float v = s_stage[i];
-                const int64_t off = (p.peer_row0 + row) * p.out_cols + (i - sl * p.out_cols);
-                for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
+            if ((p.out_cols & 3) == 0) {              // rows are multiples of 16 bytes: 512-byte requests per warp
+                const int c4 = p.out_cols >> 2;
+                for (int i = tid; i < (n >> 2); i += kThreads) {
+                    const int sl = i / c4;
+                    const int64_t row = s_rows[sl];
+                    if (row < 0) continue;
+                    const float4 v = reinterpret_cast<const float4*>(s_stage)[i];
+                    const int64_t off = (p.peer_row0 + row) * c4 + (i - sl * c4);
+                    for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_out[r])[off] = v;
+                }
+            } else {
+                for (int i = tid; i < n; i += kThreads) {
+                    const int sl = i / p.out_cols;
+                    const int64_t row = s_rows[sl];
+                    if (row < 0) continue;
+                    const float v = s_stage[i];
+                    const int64_t off = (p.peer_row0 + row) * p.out_cols + (i - sl * p.out_cols);
+                    for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
+                }
             }
         };
         // Streaming step: the team that holds a stream's first pair carries its state over -- the surviving ring rows
