@@ -755,7 +755,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 
         // =========================== DCT-II, c0 := log energy ===================================
         // one coefficient of both frames per thread (packed); threads of a quarter warp share the DCT row
-        for (int c = grp; c < p.n_out; c += geo::NGRP) {
+        // (coefficients are dealt to the thread groups from the top: the warps that were idle in the log phase -- the
+        //  highest groups -- work here, so that no warp runs both short phases and arrives late at the next tile)
+        for (int c = geo::NGRP - 1 - grp; c < p.n_out; c += geo::NGRP) {
             const float4* d4 = reinterpret_cast<const float4*>(s_dct + c * p.n_filt4);
             f2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);
             for (int m = 0; m < p.n_filt4; m += 4) {
