@@ -389,3 +389,40 @@ def test_stream_256_streams_config4():
         full = osonopy.mfcc_spec(audio_of(chunks[i].reshape(-1)), 16000, (1024, 512), 1024, 20, 20)
         want = full[total[i] - 30:total[i]]
         assert np.abs(ring[i] - want).max() <= CEP_REL * np.abs(want).max()
+
+
+def test_stream_device_push_ring_copy_and_small_ring(example_pcm):
+    """Device-pointer push (caller's ring copy + new-row counts, no host sync) equals the host-buffer push, also when a
+    step emits more frames than the ring has rows (listen.py:107-108 keeps the newest ones) and after a reset."""
+    import ctypes
+    import torch
+    from scfeat import _lib
+    _, pcm = example_pcm
+    n_streams, chunk = 3, 3000                                   # up to 6 frames per step
+    x = np.stack([np.concatenate([pcm[i], pcm[i + 4]]) for i in range(n_streams)])
+    plan = scfeat.get_plan()
+    for rows in (30, 2):
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().scf_stream_create(plan.handle, n_streams, rows, chunk, ctypes.byref(h)))
+        try:
+            d_ring = torch.full((n_streams, rows, 20), float('nan'), dtype=torch.float32, device='cuda')
+            d_new = torch.zeros((n_streams,), dtype=torch.int32, device='cuda')
+            for rep in range(2):                                 # second pass: after a reset
+                want = np.zeros((n_streams, rows, 20))
+                emitted = np.zeros(n_streams, dtype=np.int64)
+                for s in range(0, x.shape[1] - chunk + 1, chunk):
+                    d_chunk = torch.from_numpy(np.ascontiguousarray(x[:, s:s + chunk])).cuda()
+                    _lib.check(_lib.lib().scf_stream_push_i16(h, d_chunk.data_ptr(), chunk, d_ring.data_ptr(),
+                                                              d_new.data_ptr(), None))
+                    torch.cuda.synchronize()
+                    for i in range(n_streams):
+                        full = osonopy.mfcc_spec(audio_of(x[i, :s + chunk]), 16000, (1024, 512), 1024, 20, 20)
+                        k = len(full) - emitted[i]
+                        assert int(d_new[i]) == k
+                        emitted[i] = len(full)
+                        want[i] = np.concatenate([want[i], full[len(full) - k:]])[-rows:]
+                    got = d_ring.cpu().numpy()
+                    assert np.abs(got - want).max() <= CEP_REL * max(np.abs(want).max(), 1.0)
+                _lib.check(_lib.lib().scf_stream_reset(h, None))
+        finally:
+            _lib.lib().scf_stream_destroy(h)

@@ -1,8 +1,9 @@
 """Streaming feature update: the part of listen.py's Listener that is on the hot path
 (update_vectors, listen.py:96-114; buffers listen.py:88-92), for one stream or a batch of streams.
 
-State per stream lives on the GPU (carry < window samples + ring of n_features rows); each push runs
-append -> fused MFCC kernel over the carries -> ring commit (include/scfeat.h, scf_stream_*).
+State per stream lives on the GPU (carry < window samples + ring of n_features rows, double buffered); each push is
+ONE launch of the fused MFCC kernel, which reads concat(carry, chunk), writes the new ring rows and carries the state
+over (include/scfeat.h, scf_stream_*).
 use_delta is applied to the returned copy only (the reference re-applies it to the already widened
 ring every chunk, listen.py:111-112, which is a bug this does not copy).
 """
