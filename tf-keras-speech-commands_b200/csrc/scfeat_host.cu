@@ -241,7 +241,8 @@ static int upload(T** dptr, const std::vector<T>& host)
 //     kTaskBins bins (first bin even, pulled back at the end of the row, zero weights outside the segment).
 //  3. The tasks of one (segment, filter pair) form a run that accumulates in registers; long runs are split so that no
 //     run exceeds the per-group average, and runs are spread over the thread groups longest first.
-//  4. Every (run, filter) owns a partial-sum row; rows are numbered so that each filter's rows are consecutive.
+//  4. Every (run, filter) owns a partial-sum row in the exchange area; a filter's rows are consecutive inside one warp
+//     region's tail, so the log phase walks them with a fixed stride.
 struct TaskList {
     std::vector<uint32_t> words;        // grouped task words
     std::vector<int32_t> begin;         // [n_groups][2]: first and one past the last task of the group

@@ -4,19 +4,22 @@
 // common/data_utils.py:69), common/bark_feature.py:85-175 and the C++ twin
 // inference/tflite/mfcc.h:295-456.  Design notes live in DESIGN.md; the short version:
 //
-//  * One persistent CTA (8 warps) walks "tiles" of 8*G frame PAIRS (G = 32 / R, R = n_fft / 32).
-//  * FFT stage, one warp per G pairs, no CTA-level sync:
+//  * A persistent team of 8 warps walks "tiles" of 8*G frame PAIRS (G = 32 / R, R = n_fft / 32); a CTA holds one team
+//    (2 or 3 CTAs per SM) or three (one 768-thread CTA per SM).
+//  * FFT stage, one warp per G pairs, no team-level sync:
 //      two real frames A, B are packed as z = A + iB and transformed by ONE complex n_fft-point FFT,
 //      done as R-point FFTs (pass 1, lane = n2, stride-32 samples) and 32-point FFTs (pass 2,
-//      lane = k1) entirely in registers (generated straight-line code, fft_gen.cuh), with a single
-//      shared-memory transpose in between.  The two spectra are separated with the mirror identity
-//      A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i ; only the upper half of Z
-//      goes through shared memory for that.  The factor 1/2, 1/n_fft and the PCM scale are folded
-//      into the filterbank weights.
-//  * Bank stage, CTA-wide: lanes <-> frame slots, thread groups <-> host-balanced runs of the sparse
-//    filterbank (float4 smem reads of power rows and weights), partial sums to shared memory.
+//      lane = k1) entirely in registers (generated straight-line packed-FP32 code, fft_gen.cuh), with a
+//      single shared-memory transpose in between.  The two spectra are separated with the mirror identity
+//      A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i ; Z[N-k] comes from the mirror lane
+//      by warp shuffle.  The factor 1/2, 1/n_fft and the PCM scale are folded into the filterbank weights.
+//      The power spectra of the pair go to ONE shared-memory row, interleaved (|A[k]|^2, |B[k]|^2).
+//  * Bank stage, team-wide: thread = (pair slot, thread group); the host cuts the sparse filterbank into
+//    tasks of 8 bins x 2 filters (float4 reads of the pair row and of the weights, packed FMAs on both frames),
+//    balanced over the groups; partial sums to the free tail of the exchange area.
 //  * Epilogue: sum partials -> log(max(., eps)) -> DCT-II (or pass-through) -> global rows; optionally
-//    the same rows are stored to every peer GPU's cache (fused all-gather over NVLink).
+//    the same rows are stored to every peer GPU's cache (fused all-gather over NVLink), or the launch is one
+//    step of the streaming state machine (listen.py:96-114) and also carries ring and carry buffers over.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         }
     };
     if (tile_first < n_tiles) prefetch(tile_first);
-    __syncthreads();          // mbarrier init + s_logq pad rows visible (the only CTA-wide barrier)
+    __syncthreads();          // mbarrier init + zeroed s_logq pad rows visible (the only CTA-wide barrier)
 
     for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
         const uint32_t pair0 = tile * geo::PPT;
