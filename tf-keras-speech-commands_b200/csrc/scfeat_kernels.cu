@@ -811,27 +811,41 @@ static size_t smem_bytes_rt(const KParams& p)
 constexpr int64_t kTeamsMinPairs = 23040;      // measured crossover vs the 3-CTA variant: ~1500 one-second clips (tools/sweep.py)
 constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 232448;
 
-// Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM,
+// Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM (n_fft = 1024
+// only: the smaller transforms' exchange rows carry relatively more padding and do not fit three times),
 // 3 = dense with one three-team CTA per SM.  SCFEAT_VARIANT=0|1|3 forces one (tuning / A-B runs).
-int variant_for(int r, const KParams& p)
+template <int R>
+static int variant_for_r(const KParams& p)
 {
     static const int forced = [] { const char* e = getenv("SCFEAT_VARIANT"); return e ? atoi(e) : -1; }();
-    if (r != 32 || forced == 0 || !p.fast_path) return 0;     // (the generic loader needs the classic register budget)
-    const bool fits3 = smem_bytes_rt<32, 3, true>(p) <= kSmemMaxBlock;
-    const bool fits1 = 3 * (smem_bytes_rt<32, 1, true>(p) + kSmemReserve) <= kSmemPerSm;
+    if (forced == 0 || !p.fast_path) return 0;                // (the generic loader needs the classic register budget)
+    const bool fits3 = smem_bytes_rt<R, 3, true>(p) <= kSmemMaxBlock;
+    const bool fits1 = R == 32 && 3 * (smem_bytes_rt<R, 1, true>(p) + kSmemReserve) <= kSmemPerSm;
     if (forced == 3 && fits3) return 3;
     if (forced == 1 && fits1) return 1;
     if (fits3 && p.n_pairs >= kTeamsMinPairs) return 3;
     return fits1 ? 1 : 0;
 }
 
+int variant_for(int r, const KParams& p)
+{
+    return r == 32 ? variant_for_r<32>(p) : r == 16 ? variant_for_r<16>(p) : variant_for_r<8>(p);
+}
+
+template <int R>
+static size_t smem_bytes_r(const KParams& p)
+{
+    const int v = variant_for_r<R>(p);
+    if (v == 3) return smem_bytes_rt<R, 3, true>(p);
+    if constexpr (R == 32) {
+        if (v == 1) return smem_bytes_rt<R, 1, true>(p);
+    }
+    return smem_bytes_rt<R, 1, false>(p);
+}
+
 size_t extract_smem_bytes(int r, const KParams& p)
 {
-    if (r == 32) {
-        const int v = variant_for(r, p);
-        return v == 3 ? smem_bytes_rt<32, 3, true>(p) : v == 1 ? smem_bytes_rt<32, 1, true>(p) : smem_bytes_rt<32, 1, false>(p);
-    }
-    return r == 16 ? smem_bytes_rt<16, 1, false>(p) : smem_bytes_rt<8, 1, false>(p);
+    return r == 32 ? smem_bytes_r<32>(p) : r == 16 ? smem_bytes_r<16>(p) : smem_bytes_r<8>(p);
 }
 
 size_t extract_smem_limit(int r, const KParams& p)
@@ -895,18 +909,25 @@ static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_
     }
 }
 
+template <int R>
+static cudaError_t launch_extract_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
+                                    size_t smem)
+{
+    const int v = variant_for_r<R>(p);
+    if (v == 3) return launch_r<R, 3, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+    if constexpr (R == 32) {
+        if (v == 1) return launch_r<R, 1, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+    }
+    return launch_r<R, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+}
+
 cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
                            cudaStream_t st, size_t smem)
 {
     switch (r) {
-        case 32: {
-            const int v = variant_for(r, p);
-            if (v == 3) return launch_r<32, 3, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-            if (v == 1) return launch_r<32, 1, true>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-            return launch_r<32, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        }
-        case 16: return launch_r<16, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
-        case 8: return launch_r<8, 1, false>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 32: return launch_extract_r<32>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 16: return launch_extract_r<16>(is_f32, fast, p, n_tiles, num_sms, st, smem);
+        case 8: return launch_extract_r<8>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
 }

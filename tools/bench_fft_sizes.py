@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Throughput of the fast path for the three FFT sizes (window = n_fft, hop = n_fft / 2), device-resident int16 input:
+MFCC 20/20 and the reference's Bark defaults (26 filters, 13 coefficients).  Usage: python tools/bench_fft_sizes.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import scfeat
+from scfeat import _lib
+
+n = 16384
+g = torch.Generator(device='cuda')
+g.manual_seed(0)
+pcm = torch.randint(-32768, 32768, (n, 16000), dtype=torch.int16, device='cuda', generator=g)
+st = torch.cuda.current_stream()
+for n_fft in (1024, 512, 256):
+    for name, kw in (('mfcc 20/20', dict(bank=_lib.BANK_MEL_SONOPY, n_filt=20, n_coeffs=20)),
+                     ('bfcc 26/13', dict(bank=_lib.BANK_BARK_REF, n_filt=26, n_coeffs=13))):
+        plan = scfeat.get_plan(window=n_fft, hop=n_fft // 2, n_fft=n_fft, output=_lib.OUT_CEPSTRUM, **kw)
+        frames = (16000 - n_fft) // (n_fft // 2) + 1
+        out = torch.empty((n, frames, plan.out_cols), dtype=torch.float32, device='cuda')
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.extract_device(pcm.data_ptr(), n, 16000, out.data_ptr(), stream=st.cuda_stream)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        assert torch.isfinite(out).all()
+        print('n_fft %4d %-10s %6.2f G frames/s  %6.2f M clips/s  (%5.1f GB/s of PCM)' % (
+            n_fft, name, n * frames / best / 1e6, n / best / 1e3, n * 32000 / best / 1e6))
