@@ -426,3 +426,28 @@ def test_stream_device_push_ring_copy_and_small_ring(example_pcm):
                 _lib.check(_lib.lib().scf_stream_reset(h, None))
         finally:
             _lib.lib().scf_stream_destroy(h)
+
+
+def test_ragged_batch_fast_path_random_lengths(example_pcm):
+    """Per-clip lengths with front padding run on the fast kernels (predicated loads only for the pair that straddles
+    the padding): every possible alignment of the first valid sample inside a frame pair, int16 and float input."""
+    _, pcm = example_pcm
+    p = opipe.Params()
+    rng = np.random.default_rng(21)
+    n = 96
+    clips = np.stack([pcm[i % 8] for i in range(n)])
+    lengths = rng.integers(0, 16001, size=n).astype(np.int32)
+    lengths[:8] = [16000, 0, 1, 15999, 16000 - 512, 16000 - 513, 16000 - 1024, 16000 - 1025]
+    got = scfeat.data_utils.extract_features_batch(clips, lengths)[..., 0]
+    want = np.stack([opipe.audio_to_feature(audio_of(clips[i][:lengths[i]]), p) if lengths[i] > 0
+                     else opipe.audio_to_feature(np.zeros(16000, np.float32), p) for i in range(n)])
+    assert_cepstrum_close(got, want)
+    # same clips as float audio through the device API
+    import torch
+    plan = scfeat.get_plan()
+    d_in = torch.from_numpy(audio_of(clips)).cuda()
+    d_len = torch.from_numpy(lengths).cuda()
+    d_out = torch.empty((n, 30, 20), dtype=torch.float32, device='cuda')
+    plan.extract_device(d_in.data_ptr(), n, 16000, d_out.data_ptr(), d_lengths=d_len.data_ptr(), is_f32=True)
+    torch.cuda.synchronize()
+    assert_cepstrum_close(d_out.cpu().numpy(), want)

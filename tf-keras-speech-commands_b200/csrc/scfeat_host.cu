@@ -613,8 +613,9 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     magic_div((uint32_t)std::max(1, kp.pairs_per_clip), kp.ppc_magic, kp.ppc_shift);
     const int ppt = pairs_per_tile(plan->radix_r);
     n_tiles = (kp.n_pairs + ppt - 1) / ppt;
-    fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && d_lengths == nullptr && c.preemph_alpha == 0.f &&
-           c.window_fn == SCF_WIN_RECT;
+    // the fast kernels also take short clips that are zero-padded in front (common/data_utils.py:77-80)
+    fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && (d_lengths == nullptr || pad == SCF_PAD_FRONT_ZERO) &&
+           c.preemph_alpha == 0.f && c.window_fn == SCF_WIN_RECT;
     return SCF_OK;
 }
 

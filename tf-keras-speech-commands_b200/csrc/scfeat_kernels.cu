@@ -319,22 +319,28 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         q_out = gp - c_out * ppc;
     };
 
-    // fast path (window == n_fft, hop == n_fft/2, full-length clips): frames 2q and 2q+1 share half their samples;
-    // raw[j] = x[n_fft*q + lane + 32 j], j < R + R/2.  Frame B is absent only for the last pair of a clip with an odd
-    // frame count: its upper samples may lie behind the clip and are not touched.
+    // fast path (window == n_fft, hop == n_fft/2): frames 2q and 2q+1 share half their samples;
+    // raw[j] = x[n_fft*q + lane + 32 j], j < R + R/2.  Two rare cases take the predicated form of the loop:
+    //  * frame B is absent (last pair of a clip with an odd frame count): its upper samples may lie behind the clip;
+    //  * the pair touches the zeros in FRONT of a short clip (per-clip lengths with SCF_PAD_FRONT_ZERO,
+    //    common/data_utils.py:77-80): element e of the padded clip is sample e - pad of the clip's data.
     typedef typename Raw<InT>::type RawT;
     RawT raw[geo::G][geo::NLOAD];
     auto load_pair = [&](uint32_t clip, uint32_t q, RawT (&dst)[geo::NLOAD]) {
-        const InT* __restrict__ src = in + (int64_t)clip * p.clip_stride + q * geo::NFFT + lane;
-        auto ld = [&](const InT* a) { return ld_sample(a); };
-        if (__builtin_expect((int)(2 * q + 1) < p.frames_per_clip, 1)) {
+        int pad = 0;
+        if (p.lengths != nullptr) pad = p.clip_len - min(max(__ldg(p.lengths + clip), 0), p.clip_len);
+        const int e0 = (int)q * geo::NFFT;                    // first element of the pair in the padded clip
+        const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
+        const int n_ld = ((int)(2 * q + 1) < p.frames_per_clip) ? geo::NLOAD : R;
+        if (__builtin_expect(pad <= e0 && n_ld == geo::NLOAD, 1)) {
+            const InT* __restrict__ src = cb + (e0 - pad) + lane;
 #pragma unroll
-            for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld(src + 32 * j);
+            for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld_sample(src + 32 * j);
         } else {
+            const int j0 = (pad - e0 - lane + 31) >> 5;       // first j with e0 + lane + 32 j >= pad
 #pragma unroll
-            for (int j = 0; j < R; ++j) dst[j] = ld(src + 32 * j);
-#pragma unroll
-            for (int j = R; j < geo::NLOAD; ++j) dst[j] = (RawT)0;
+            for (int j = 0; j < geo::NLOAD; ++j)
+                dst[j] = (j >= j0 && j < n_ld) ? ld_sample(cb + (e0 - pad + lane + 32 * j)) : (RawT)0;
         }
     };
     // classic variant: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases of
