@@ -83,6 +83,23 @@ __device__ __forceinline__ int32_t ld_sample(const int16_t* p)
     return v;
 }
 __device__ __forceinline__ float ld_sample(const float* p) { return __ldg(p); }
+// ... predicated: nothing is read and zero is returned when `on` is false (the address may then lie outside the buffer)
+__device__ __forceinline__ int32_t ld_sample_if(const int16_t* p, bool on)
+{
+    int32_t v;
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n mov.b32 %0, 0;\n @q ld.global.nc.s16 %0, [%1];\n}"
+                 : "=r"(v) : "l"(p), "r"((int)on));
+    return v;
+}
+__device__ __forceinline__ float ld_sample_if(const float* p, bool on)
+{
+    float v;
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n mov.b32 %0, 0;\n @q ld.global.nc.f32 %0, [%1];\n}"
+                 : "=f"(v) : "l"(p), "r"((int)on));
+    return v;
+}
+__device__ __forceinline__ int32_t raw_or(int32_t a, int32_t b) { return a | b; }
+__device__ __forceinline__ float raw_or(float a, float b) { return a + b; }      // one of them is 0
 // bits that are set iff the sample is not zero (-0.0f counts as zero)
 __device__ __forceinline__ uint32_t nz_bits(int32_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
@@ -119,51 +136,70 @@ __device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
 }
 
 // Generic loader: any window / hop / per-clip length / pre-emphasis / window function; loads the two frames of a pair.
-// Sample a of the clip comes from clip_base[a] for a < split and from tail[a - split] behind it (streaming: carry,
-// then the new chunk).  Branch-free: every lane issues all its loads of BOTH frames back to back (out-of-range
-// positions read clip_base[0], which always exists, and are zeroed afterwards), so the memory latency is paid once
-// per pair, not once per sample.
-template <int R, typename InT>
+// Sample a of the clip comes from clip_base[a] for a < split and from tail[a - split] behind it (STREAM: carry, then
+// the new chunk).  Every lane issues all its loads of BOTH frames back to back as predicated loads off two base
+// pointers with immediate offsets (no per-sample address arithmetic; out-of-range positions read nothing and are
+// zero), so the memory latency is paid once per pair, not once per sample.
+template <int R, typename InT, bool STREAM>
 __device__ __forceinline__ void load_pair_generic(const KParams& p, const InT* __restrict__ clip_base,
                                                   const InT* __restrict__ tail, int split, const ClipGeom& cg, int frame_a,
                                                   int lane, float (&xa)[R], float (&xb)[R], uint32_t& nz_a, uint32_t& nz_b)
 {
     typedef typename Raw<InT>::type RawT;
-    auto pos = [&](int i) { return lane + 32 * scf_bitrev(i, Geo<R>::LOG2R); };
-    auto in_range = [&](int frame, int n) {
-        const int a = frame * p.hop - cg.pad + n;         // index in the clip's own data
-        return frame < cg.n_frames && n < p.w_eff && a >= 0 && a < cg.len;
+    // frame f covers clip samples s0 + n, n < w_eff; n is valid for lo <= n < lo + width
+    struct Span { int s0, lo; unsigned width; };
+    auto span_of = [&](int frame) {
+        Span sp;
+        sp.s0 = frame * p.hop - cg.pad;
+        sp.lo = max(0, -sp.s0);
+        const int hi = frame < cg.n_frames ? min(p.w_eff, cg.len - sp.s0) : 0;
+        sp.width = (unsigned)max(0, hi - sp.lo);
+        return sp;
     };
-    auto addr = [&](int a) { return a < split ? clip_base + a : tail + (a - split); };
-    auto fetch = [&](int frame, int back, RawT (&raw)[R]) {
+    const Span sa = span_of(frame_a), sb = span_of(frame_a + 1);
+    auto fetch = [&](const Span& sp, int back, RawT (&raw)[R]) {
+        const InT* p0 = clip_base + (sp.s0 - back) + lane;               // sample a - back for n = lane
+        const InT* p1 = tail + (sp.s0 - back - split) + lane;
+        const int rel = lane - sp.lo;                                     // n - lo for n = lane
+        const int a0 = sp.s0 - back + lane;                               // a - back for n = lane
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const int n = pos(i), a = frame * p.hop - cg.pad + n - back;
-            raw[i] = ld_sample(in_range(frame, n) && a >= 0 ? addr(a) : clip_base);
+            const int o = 32 * scf_bitrev(i, Geo<R>::LOG2R);
+            const bool in = (unsigned)(rel + o) < sp.width && a0 + o >= 0;
+            if constexpr (STREAM) {
+                const bool first = a0 + o < split;
+                raw[i] = raw_or(ld_sample_if(p0 + o, in && first), ld_sample_if(p1 + o, in && !first));
+            } else {
+                raw[i] = ld_sample_if(p0 + o, in);
+            }
         }
     };
     RawT ra[R], rb[R];
-    fetch(frame_a, 0, ra);
-    fetch(frame_a + 1, 0, rb);
+    fetch(sa, 0, ra);
+    fetch(sb, 0, rb);
 #pragma unroll
     for (int i = 0; i < R; ++i) { xa[i] = to_f32(ra[i]); xb[i] = to_f32(rb[i]); }
     if (p.preemph != 0.f) {                                   // x[a] - alpha * x[a-1], x[-1] := 0 (mfcc.h:394-403)
-        fetch(frame_a, 1, ra);
-        fetch(frame_a + 1, 1, rb);
+        fetch(sa, 1, ra);
+        fetch(sb, 1, rb);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const int n = pos(i);
-            if (frame_a * p.hop - cg.pad + n >= 1) xa[i] = fmaf(-p.preemph, to_f32(ra[i]), xa[i]);
-            if ((frame_a + 1) * p.hop - cg.pad + n >= 1) xb[i] = fmaf(-p.preemph, to_f32(rb[i]), xb[i]);
+            xa[i] = fmaf(-p.preemph, to_f32(ra[i]), xa[i]);
+            xb[i] = fmaf(-p.preemph, to_f32(rb[i]), xb[i]);
+        }
+    }
+    if (p.win != nullptr) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int n = lane + 32 * scf_bitrev(i, Geo<R>::LOG2R);
+            const float w = ld_sample_if(p.win + n, n < p.w_eff);
+            xa[i] *= w;
+            xb[i] *= w;
         }
     }
     nz_a = nz_b = 0;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const int n = pos(i);
-        const float w = (p.win != nullptr && n < p.w_eff) ? __ldg(p.win + n) : 1.f;
-        xa[i] = in_range(frame_a, n) ? xa[i] * w : 0.f;
-        xb[i] = in_range(frame_a + 1, n) ? xb[i] * w : 0.f;
         nz_a |= nz_bits(xa[i]);
         nz_b |= nz_bits(xb[i]);
     }
@@ -420,16 +456,18 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
                         const ClipGeom cg = clip_geom(p, clip);
                         n_frames = cg.n_frames;
-                        const InT* tail = cb;
-                        int split = 0x7fffffff;
-                        if constexpr (sizeof(InT) == 2) {
-                            if (p.stream_on) {
-                                split = cg.len - p.stream.chunk_len;
-                                tail = reinterpret_cast<const InT*>(p.stream.chunks) + (int64_t)clip * p.stream.chunk_len;
-                            }
-                        }
                         float xr[R], xi[R];
-                        load_pair_generic<R, InT>(p, cb, tail, split, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
+                        bool streaming = false;
+                        if constexpr (sizeof(InT) == 2) streaming = p.stream_on != 0;
+                        if (streaming) {
+                            if constexpr (sizeof(InT) == 2) {
+                                const int split = cg.len - p.stream.chunk_len;          // carry, then the new chunk
+                                const InT* tail = reinterpret_cast<const InT*>(p.stream.chunks) + (int64_t)clip * p.stream.chunk_len;
+                                load_pair_generic<R, InT, true>(p, cb, tail, split, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
+                            }
+                        } else {
+                            load_pair_generic<R, InT, false>(p, cb, cb, 0, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
+                        }
 #pragma unroll
                         for (int i = 0; i < R; ++i) x[i] = pk(xr[i], xi[i]);
                     }
