@@ -111,6 +111,26 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers allocated
+    afterwards sit on the GPU's own NUMA node (with 8 ranks on a two-socket box remote buffers halve the upload rate).
+    Returns (cpus now allowed, cpus allowed before) or (None, before) when nothing was changed."""
+    before = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        use = local & before
+        if use and use != before:
+            os.sched_setaffinity(0, use)
+            return use, before
+    except Exception:
+        pass
+    return None, before
+
+
 def _cpu_worker_init():
     for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[k] = '1'
@@ -248,6 +268,7 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: libscfeat has no CPU fallback')
+    bound, all_cpus = bind_to_gpu_numa(local_rank)        # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -349,7 +370,7 @@ def run_ours(args):
     d_tmp = torch.empty((CLIPS_PER_STEP, CLIP_LEN), dtype=torch.int16, device='cuda')
     d_feat = torch.empty((CLIPS_PER_STEP, FRAMES, COLS), dtype=torch.float32, device='cuda')
     s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
-    torch.cuda.synchronize()
+    barrier()                    # all ranks copy at the same time: the floor under the same host contention as e2e
     t0 = time.perf_counter()
     for i in range(40):          # uploads and downloads on separate streams: the full-duplex PCIe floor
         with torch.cuda.stream(s_up):
@@ -359,10 +380,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     copy_s = (time.perf_counter() - t0) / 40
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    times = torch.tensor([ms, e2e_s * 1e3, copy_s], dtype=torch.float64, device='cuda')
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(times[0]), float(times[1])
+    ms, e2e_ms, copy_s = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         peaks, peaks_src = read_peaks()
@@ -370,6 +391,7 @@ def run_ours(args):
         launch_s = ms * 1e-3 / K
         hbm_achieved = CLIPS_PER_STEP * BYTES_PER_CLIP / launch_s / 1e9
         fp32_achieved = CLIPS_PER_STEP * FLOPS_PER_CLIP / launch_s
+        os.sched_setaffinity(0, all_cpus)                 # the CPU baseline uses every core the job may use
         cpu = run_cpu_baseline() if world == 1 else None
         line = {
             'metric': 'features clips/sec (1 s, 16 kHz)', 'value': clips_per_s, 'unit': 'clips/s',
@@ -396,6 +418,7 @@ def run_ours(args):
                     'steps': Ke, 'pcie_copy_only_clips_per_s': world * CLIPS_PER_STEP / copy_s,
                     'pcie_h2d_gbs': CLIPS_PER_STEP * CLIP_LEN * 2 / copy_s / 1e9,
                     'sync_call_clips_per_s': world * CLIPS_PER_STEP / sync_call_s,
+                    'host_cpus_bound_to_gpu_numa_node': (len(bound) if bound else None),
                     'api': 'Plan.extract_host_async + host_sync -> scf_extract_host_i16_async (pinned host int16 in, pinned host '
                            'float32 out, two staging slots); sync_call = Plan.extract_host(out=), one blocking call per step'},
             'clips_per_s_single_launch': big_batches,
