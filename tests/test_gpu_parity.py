@@ -451,3 +451,41 @@ def test_ragged_batch_fast_path_random_lengths(example_pcm):
     plan.extract_device(d_in.data_ptr(), n, 16000, d_out.data_ptr(), d_lengths=d_len.data_ptr(), is_f32=True)
     torch.cuda.synchronize()
     assert_cepstrum_close(d_out.cpu().numpy(), want)
+
+
+def test_one_plan_shared_by_threads_and_streams(example_pcm):
+    """include/scfeat.h: plans are immutable and may be shared between threads.  Four threads drive the same plan on
+    their own CUDA streams (device API) and through the host-buffer API at once; every result must equal the
+    single-threaded one bit for bit."""
+    import threading
+    import torch
+    _, pcm = example_pcm
+    plan = scfeat.get_plan()
+    rng = np.random.default_rng(5)
+    batches = [rng.integers(-32768, 32768, size=(64 + 32 * t, 16000), dtype=np.int16) for t in range(4)]
+    want = [plan.extract_host(b) for b in batches]
+    got_dev, got_host, errs = [None] * 4, [None] * 4, []
+
+    def work(t):
+        try:
+            st = torch.cuda.Stream()
+            d_in = torch.from_numpy(batches[t]).cuda()
+            d_out = torch.empty((len(batches[t]), 30, 20), dtype=torch.float32, device='cuda')
+            for _ in range(20):
+                plan.extract_device(d_in.data_ptr(), len(batches[t]), 16000, d_out.data_ptr(), stream=st.cuda_stream)
+            st.synchronize()
+            got_dev[t] = d_out.cpu().numpy()
+            for _ in range(3):
+                got_host[t] = plan.extract_host(batches[t])
+        except Exception as e:      # surfaced below: an exception in a thread must fail the test
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for t in range(4):
+        np.testing.assert_array_equal(got_dev[t], want[t])
+        np.testing.assert_array_equal(got_host[t], want[t])
