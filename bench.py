@@ -38,7 +38,7 @@ COLS = 20
 BYTES_PER_CLIP = 32000 + 2400
 FLOPS_PER_CLIP = 925200
 FP32_NOMINAL = 148 * 128 * 2 * 1.965e9
-NCU_DRAM_BYTES_PER_LAUNCH = 16342272   # measured once with ncu, see roofline.traffic_source
+NCU_DRAM_BYTES_PER_LAUNCH = 16349440   # measured once with ncu, see roofline.traffic_source
 
 
 def read_peaks():
@@ -403,7 +403,7 @@ def run_ours(args):
                        'l2_policy': 'pool of 16 distinct 16.4 MB input batches (262 MB > 126 MB L2) rotated per step'},
             'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                          'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': NCU_DRAM_BYTES_PER_LAUNCH, 'peak_source': peaks_src,
-                         'traffic_source': 'profiles/r01_v8_b512_metrics.csv (ncu --set full: dram__bytes_read.sum 16,342,272 + '
+                         'traffic_source': 'profiles/r01_v13_b512_metrics.csv (ncu --set full: dram__bytes_read.sum 16,349,440 + '
                                            'dram__bytes_write.sum 0 per 512-clip launch; the 1.2 MB of output is still in L2 when '
                                            'the kernel ends)',
                          'kernel': 'scf::extract_kernel<32, short, fast, 1 team, dense> (3 CTAs/SM, 80 registers)', 'algorithmic_bytes_per_launch': CLIPS_PER_STEP * BYTES_PER_CLIP,
