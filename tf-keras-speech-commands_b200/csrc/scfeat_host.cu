@@ -579,7 +579,6 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.frames_per_clip = (int32_t)scf_num_frames(clip_len, c.window, c.hop);
     kp.pairs_per_clip = (kp.frames_per_clip + 1) / 2;
     kp.n_pairs = n_clips * (int64_t)kp.pairs_per_clip;
-    kp.n_clips_lo = (int32_t)n_clips;
     kp.window = c.window;
     kp.hop = c.hop;
     kp.w_eff = std::min(c.window, c.n_fft);
@@ -604,9 +603,7 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.off_tasks = plan->off_tasks;
     kp.off_tbeg = plan->off_tbeg;
     kp.off_qspec = plan->off_qspec;
-    kp.n_tasks = plan->n_tasks;
     kp.n_q = plan->n_q;
-    kp.n_dst = plan->n_dst;
     kp.n_filt = c.n_filt;
     kp.n_filt4 = plan->n_filt4;
     kp.n_out = plan->n_out;

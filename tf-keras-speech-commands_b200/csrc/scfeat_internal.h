@@ -70,7 +70,6 @@ struct KParams {
     const void* in;              // int16_t* or float*
     int64_t clip_stride;         // elements between clips
     int64_t n_pairs;             // n_clips * pairs_per_clip
-    int32_t n_clips_lo;          // (unused high bits guard) n_clips fits int32 for every config
     int32_t clip_len;            // samples per (padded) clip
     const int32_t* lengths;      // nullable
     int32_t pad_mode;            // scf_pad_kind
@@ -95,9 +94,7 @@ struct KParams {
     int32_t table_bytes;         // whole blob
     int32_t table_small_bytes;   // leading part without twiddles / DCT (what the 3-CTA-per-SM kernels stage)
     int32_t off_wts, off_tw, off_dct, off_tasks, off_tbeg, off_qspec;
-    int32_t n_tasks;
     int32_t n_q;                 // n_filt (+1 when the cepstrum needs the frame energy)
-    int32_t n_dst;               // number of partial-sum rows in use (informational)
     int32_t n_filt;
     int32_t n_filt4;             // n_filt rounded up to a multiple of 4
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)
