@@ -7,14 +7,20 @@
 One "step" = one pass of the hot path over one batch of 512 synthetic clips (BASELINE config 2, train.py's default
 batch) per GPU: a single fused kernel launch.  Prints ONE JSON line on rank 0.
 
-  value         whole-job clips/s, inputs resident in HBM, CUDA events around exactly K back-to-back steps,
-                max over ranks.  A pool of distinct input batches larger than L2 is rotated so that no step finds
-                its input in L2.
+  value         whole-job clips/s, inputs resident in HBM.  The K steps are captured ONCE into a CUDA graph (K kernel
+                nodes joined by programmatic-dependent-launch edges) so that the timed region holds no host work: CUDA
+                events around one replay = exactly K back-to-back steps, barrier + synchronize on both sides, max over
+                ranks; the median of 5 such replays is reported (all five are listed).  A pool of distinct input
+                batches larger than L2 is rotated so that no step finds its input in L2.  The same K steps issued
+                from Python (one ctypes call per step) are timed beside it ("issue_loop").
+  config3       BASELINE configs[2]: the 105,829-clip corpus sharded over the ranks -- extract only, fused extract +
+                all-gather through NVLink peer stores, extract + ncclAllGather; bit-exact check of every rank's cache;
+                gather-inclusive scaling efficiency against the whole corpus on one GPU (measured on rank 0).
   e2e           same metric through the public host-buffer API (plan.extract_host -> scf_extract_host_i16):
                 pinned host int16 in, H2D + kernel + D2H inside the timed region, every step.
-  roofline      the kernel against the measured HBM peak (algorithmic 34,400 B per clip) and, under "fp32", against
-                the FP32 compute roofline that actually binds (925,200 algorithmic FLOP per clip; peak = FMA
-                micro-benchmark measured in this run, nominal 74.45 TFLOP/s beside it).
+  roofline      the kernel against the roofline that binds: FP32 compute (925,200 algorithmic FLOP per clip; peak = FMA
+                micro-benchmark measured in this run, nominal 74.45 TFLOP/s beside it); the HBM side (34,400 algorithmic
+                bytes per clip against the measured copy bandwidth) is nested under "hbm".
   cpu_baseline  the oracle's numpy restatement of the reference's sonopy path on the host cores (bounded sample).
 
 --impl reference times the reference's own CPU implementation of the path: the numpy/sonopy restatement in
@@ -31,6 +37,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOAD = ('configs[1]: batch of 512 synthetic 1 s 16 kHz int16 clips (uniform random, numpy default_rng) per step, '
+            'params.json MFCC (window 1024, hop 512, n_fft 1024, 20 mel filters, 20 coefficients -> 30x20)')
+CORPUS_CLIPS = 105829                  # configs[2]: Speech Commands v0.02 size
 CLIPS_PER_STEP = 512
 CLIP_LEN = 16000
 FRAMES = 30
@@ -38,7 +47,9 @@ COLS = 20
 BYTES_PER_CLIP = 32000 + 2400
 FLOPS_PER_CLIP = 925200
 FP32_NOMINAL = 148 * 128 * 2 * 1.965e9
-NCU_DRAM_BYTES_PER_LAUNCH = 16349440   # measured once with ncu, see roofline.traffic_source
+NCU_DRAM_BYTES_PER_LAUNCH = 16349440   # measured once with ncu, see NCU_TRAFFIC_SOURCE
+NCU_TRAFFIC_SOURCE = ('profiles/r01_v13_b512_metrics.csv (ncu --set full: dram__bytes_read.sum 16,349,440 + '
+                      'dram__bytes_write.sum 0 per 512-clip launch; the 1.2 MB of output is still in L2 when the kernel ends)')
 
 
 def read_peaks():
@@ -245,8 +256,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'features clips/sec (1 s, 16 kHz)', 'value': value, 'unit': 'clips/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: batch of 512 synthetic 1 s 16 kHz int16 clips, params.json MFCC (30x20)',
-                   'sample_clips_per_step': per_step},
+        'config': {'workload': WORKLOAD, 'sample_clips_per_step': per_step},
         'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': n_proc, 'kind': 'port',
                          'sample': '%d clips per step; numpy restatement (oracle/sonopy.py) of the reference Python path '
                                    'common/data_utils.py:69 -> sonopy.mfcc_spec, %d processes' % (per_step, n_proc),
@@ -255,6 +265,120 @@ def run_reference(args):
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_config3(plan, rank, world, local_rank, dist, st):
+    """BASELINE configs[2]: the 105,829-clip corpus sharded over the ranks (rank r owns clips [r*ceil(N/R), ...)), every
+    rank ends up with the whole [N, 30, 20] feature cache.  Times (CUDA events, best of 5, max over ranks) the
+    extraction alone, the fused extraction + all-gather (the kernel epilogue stores every row into all ranks' caches
+    through NVLink peer mappings, scf_extract_i16_gather) and extraction followed by ncclAllGather; checks that every
+    rank's cache equals what the owning rank computes locally, bit for bit.  Returns the "config3" object (rank 0)."""
+    import numpy as np
+    import torch
+    from scfeat.dist import FeatureCacheGather, shard_range
+    n = CORPUS_CLIPS
+    start, count, per = shard_range(n, world, rank)
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1000 + rank)
+    d_pcm = torch.randint(-32768, 32768, (max(count, 1), CLIP_LEN), dtype=torch.int16, device='cuda', generator=g)
+    group = dist.group.WORLD if dist is not None else None
+    cache = FeatureCacheGather(plan, n, CLIP_LEN, world, rank, local_rank, group=group)
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps=5):
+        best = None
+        for _ in range(reps):
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            fn()
+            e1.record(st)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t[0]) if best is None else min(best, float(t[0]))
+        return best
+
+    with torch.cuda.stream(st):
+        local_out = torch.empty((per, FRAMES, COLS), dtype=torch.float32, device='cuda')
+        full = torch.empty((world * per, FRAMES, COLS), dtype=torch.float32, device='cuda')
+        # ---- correctness: my cache's block of every rank equals what that rank computes locally -----------------
+        sync()
+        cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream)
+        sync()
+        local_out.zero_()
+        plan.extract_device(d_pcm.data_ptr(), count, CLIP_LEN, local_out.data_ptr(), stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.all_gather_into_tensor(full, local_out)
+        else:
+            full.copy_(local_out)
+        torch.cuda.synchronize()
+        got = cache.to_host()
+        ok = bool(np.array_equal(got, full[:n].cpu().numpy())) and bool(np.isfinite(got).all())
+        flag = torch.tensor([1 if ok else 0], device='cuda')
+        if dist is not None:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        del got
+        # ---- timings --------------------------------------------------------------------------------------------
+        t_extract = timed(lambda: plan.extract_device(d_pcm.data_ptr(), count, CLIP_LEN, local_out.data_ptr(), stream=st.cuda_stream))
+        t_fused = timed(lambda: cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream))
+        t_nccl = None
+        if dist is not None:
+            def nccl_path():
+                plan.extract_device(d_pcm.data_ptr(), count, CLIP_LEN, local_out.data_ptr(), stream=st.cuda_stream)
+                dist.all_gather_into_tensor(full, local_out)
+            t_nccl = timed(nccl_path)
+        # ---- the whole corpus on ONE GPU (rank 0; the other ranks wait): the N = 1 point of the efficiency ------
+        t_single = None
+        del full, local_out, d_pcm
+        cache.close()
+        torch.cuda.empty_cache()
+        if world == 1:
+            t_single = t_extract
+        else:
+            if rank == 0:
+                d_all = torch.randint(-32768, 32768, (n, CLIP_LEN), dtype=torch.int16, device='cuda', generator=g)
+                d_all_out = torch.empty((n, FRAMES, COLS), dtype=torch.float32, device='cuda')
+                best = None
+                for _ in range(5):
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    plan.extract_device(d_all.data_ptr(), n, CLIP_LEN, d_all_out.data_ptr(), stream=st.cuda_stream)
+                    e1.record(st)
+                    torch.cuda.synchronize()
+                    t = e0.elapsed_time(e1)
+                    best = t if best is None else min(best, t)
+                t_single = best
+                del d_all, d_all_out
+                torch.cuda.empty_cache()
+            sync()
+    if rank != 0:
+        return None
+    out = {
+        'workload': 'configs[2]: %d synthetic 1 s clips sharded over %d GPU(s) (%d per rank), every rank ends with the whole '
+                    '[N, 30, 20] feature cache' % (n, world, per),
+        'ok_bit_exact_on_every_rank': bool(int(flag[0])),
+        'extract_only_ms': t_extract, 'fused_extract_gather_ms': t_fused, 'extract_plus_nccl_allgather_ms': t_nccl,
+        'extract_only_clips_per_s': n / (t_extract * 1e-3), 'fused_clips_per_s': n / (t_fused * 1e-3),
+        'single_gpu_whole_corpus_ms': t_single,
+        'efficiency_extract_only_vs_1gpu': t_single / (world * t_extract),
+        'efficiency_gather_inclusive_vs_1gpu': t_single / (world * t_fused),
+        'timing': 'CUDA events on the launching stream, best of 5, max over ranks; inputs resident in HBM (423 MB per rank at 8)',
+    }
+    if world > 1:
+        # the gather's own roofline: every rank sends its 31.7 MB shard to world-1 peers and receives theirs
+        sent = per * FRAMES * COLS * 4 * (world - 1)
+        out['nvlink_bytes_sent_per_rank'] = sent
+        out['gather_floor_ms_at_770GBs'] = sent / 770e9 * 1e3
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -300,21 +424,51 @@ def run_ours(args):
 
     fp32_peak = scfeat.measure_fp32_flops(local_rank)
 
+    def timed_region(fn):
+        """barrier + synchronize, CUDA events on the launching stream around fn(), barrier + synchronize; ms"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        fn()
+        e1.record(st)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     with torch.cuda.stream(st):
         for i in range(W):
             step(i)
         barrier()
-        launches0 = scfeat.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # ---- the K steps issued from Python, one ctypes call each (secondary number) -----------------------
         sampler.busy(True)
-        e0.record(st)
-        for i in range(K):
-            step(W + i)
-        e1.record(st)
-        barrier()
+        loop_ms = max_over_ranks(timed_region(lambda: [step(W + i) for i in range(K)]))
+        # ---- the same K steps as ONE CUDA graph: no host work inside the timed region ----------------------
+        graph, timing = None, 'cuda-graph'
+        launches0 = scfeat.launch_count()
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=st, capture_error_mode='thread_local'):
+                for i in range(K):
+                    plan.extract_device(ptrs[(W + i) % n_pool], CLIPS_PER_STEP, CLIP_LEN, d_out.data_ptr(),
+                                        stream=torch.cuda.current_stream().cuda_stream)
+        except Exception as exc:                                  # no capture: keep the issue-loop number
+            graph, timing = None, 'stream issue loop (graph capture failed: %s)' % str(exc)[:120]
+        launches = scfeat.launch_count() - launches0              # kernel nodes of the graph = launches per replay
+        replays = []
+        if graph is not None:
+            for _ in range(2):
+                graph.replay()
+            for _ in range(5):
+                replays.append(max_over_ranks(timed_region(graph.replay)))
+            ms = sorted(replays)[len(replays) // 2]
+        else:
+            ms, launches = loop_ms, K
         sampler.busy(False)
-        launches = scfeat.launch_count() - launches0
-        ms = e0.elapsed_time(e1)
 
     # parity spot check of the timed configuration (last batch computed) -- outside the timed region
     got = d_out.cpu().numpy()
@@ -336,7 +490,7 @@ def run_ours(args):
                     t = b0.elapsed_time(b1)
                     best = t if best is None else min(best, t)
                 big_batches[str(n)] = n / (best * 1e-3)
-        del d_big
+        del d_big, flat
 
     # ---- e2e: host buffers through the public API, H2D + kernel + D2H every step -----------------------------
     n_hpool = 4
@@ -380,10 +534,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     copy_s = (time.perf_counter() - t0) / 40
 
-    times = torch.tensor([ms, e2e_s * 1e3, copy_s], dtype=torch.float64, device='cuda')
+    times = torch.tensor([e2e_s * 1e3, copy_s], dtype=torch.float64, device='cuda')
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, copy_s = float(times[0]), float(times[1]), float(times[2])
+    e2e_ms, copy_s = float(times[0]), float(times[1])
+    del d_tmp, d_feat, d_pool
+    torch.cuda.empty_cache()
+    config3 = run_config3(plan, rank, world, local_rank, dist, st)
 
     if rank == 0:
         peaks, peaks_src = read_peaks()
@@ -397,21 +554,25 @@ def run_ours(args):
             'metric': 'features clips/sec (1 s, 16 kHz)', 'value': clips_per_s, 'unit': 'clips/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: batch of 512 synthetic 1 s 16 kHz int16 clips per GPU, params.json MFCC '
-                                   '(window 1024, hop 512, n_fft 1024, 20 mel filters, 20 coefficients -> 30x20)',
-                       'clips_per_step_per_gpu': CLIPS_PER_STEP, 'parallelism': 'clip-sharded x%d, no collective' % world,
-                       'l2_policy': 'pool of 16 distinct 16.4 MB input batches (262 MB > 126 MB L2) rotated per step'},
-            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': NCU_DRAM_BYTES_PER_LAUNCH, 'peak_source': peaks_src,
-                         'traffic_source': 'profiles/r01_v13_b512_metrics.csv (ncu --set full: dram__bytes_read.sum 16,349,440 + '
-                                           'dram__bytes_write.sum 0 per 512-clip launch; the 1.2 MB of output is still in L2 when '
-                                           'the kernel ends)',
-                         'kernel': 'scf::extract_kernel<32, short, fast, 1 team, dense> (3 CTAs/SM, 80 registers)', 'algorithmic_bytes_per_launch': CLIPS_PER_STEP * BYTES_PER_CLIP,
-                         'binding': 'fp32 (SURVEY 8d: 26.9 flop/B > machine balance), see "fp32"',
-                         'fp32': {'achieved': fp32_achieved / 1e12, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
-                                  'frac': fp32_achieved / fp32_peak, 'peak_source': 'FMA micro-benchmark in this run',
-                                  'nominal_peak': FP32_NOMINAL / 1e12, 'frac_of_nominal': fp32_achieved / FP32_NOMINAL,
-                                  'algorithmic_flops_per_launch': CLIPS_PER_STEP * FLOPS_PER_CLIP}},
+            'config': {'workload': WORKLOAD,
+                       'clips_per_step_per_gpu': CLIPS_PER_STEP, 'parallelism': 'clip-sharded x%d, no collective in the step '
+                       '(the corpus all-gather is measured under "config3")' % world,
+                       'l2_policy': 'pool of 16 distinct 16.4 MB input batches (262 MB > 126 MB L2) rotated per step',
+                       'timing': timing, 'timed_replays_ms': replays, 'issue_loop_ms_per_step': loop_ms / K,
+                       'issue_loop_clips_per_s': world * CLIPS_PER_STEP * K / (loop_ms * 1e-3)},
+            'roofline': {'bound': 'fp32', 'achieved': fp32_achieved / 1e12, 'peak': fp32_peak / 1e12, 'unit': 'TFLOP/s',
+                         'frac': fp32_achieved / fp32_peak,
+                         'peak_source': 'FP32 FMA micro-benchmark measured in this run (MEASURED_PEAKS.json holds no FP32 figure)',
+                         'nominal_peak': FP32_NOMINAL / 1e12, 'frac_of_nominal': fp32_achieved / FP32_NOMINAL,
+                         'algorithmic_flops_per_launch': CLIPS_PER_STEP * FLOPS_PER_CLIP,
+                         'traffic': NCU_DRAM_BYTES_PER_LAUNCH,
+                         'traffic_source': NCU_TRAFFIC_SOURCE,
+                         'kernel': 'scf::extract_kernel<32, short, fast, 1 team, dense> (3 CTAs/SM, 80 registers)',
+                         'why_fp32': 'SURVEY 8d: 26.9 flop/B > machine balance 11.4 flop/B, so FP32 compute binds, not HBM',
+                         'hbm': {'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                 'frac': hbm_achieved / peaks['hbm_gbs'], 'peak_source': peaks_src,
+                                 'algorithmic_bytes_per_launch': CLIPS_PER_STEP * BYTES_PER_CLIP}},
+            'config3': config3,
             'cpu_baseline': cpu,
             'e2e': {'value': world * CLIPS_PER_STEP * Ke / (e2e_ms * 1e-3), 'unit': 'clips/s',
                     'h2d_bytes_per_step': CLIPS_PER_STEP * CLIP_LEN * 2, 'd2h_bytes_per_step': CLIPS_PER_STEP * FRAMES * COLS * 4,

@@ -12,6 +12,7 @@ Parity status (see DESIGN.md "Oracle"):
     it, so it is pinned indirectly: against the in-tree C++ twin inference/tflite/mfcc.h
     compiled into oracle/_ref (max |diff| <= 6e-7 on all example/*.wav), and against
     bark_feature.py's verbatim copies of sonopy's chop_array/power_spec/safe_log.
-    "parity unpinned" applies only to sonopy's ``correct_grid`` de-duplication, which no
-    BASELINE config exercises.
+    Mel grids with repeated points (e.g. n_fft 512 with 40 filters) follow the C++ twin, which keeps
+    them (sonopy's ``correct_grid`` helper is a no-op as published, see oracle/sonopy.py mel_grid);
+    that case is pinned against the twin as well (bank and features).
 """

@@ -61,24 +61,20 @@ def mels_to_hertz(m):
     return 700.0 * (np.exp(m / 1127.0) - 1.0)    # mfcc.h:141-145
 
 
-def _dedup_forward(points):
-    """sonopy's correct_grid: push repeated grid indices forward so no filter is empty."""
-    out, offset, prev = [], 0, points[0] - 1
-    for p in points:
-        offset = max(0, offset + prev + 1 - p)
-        out.append(p + offset)
-        prev = p
-    return out
-
-
 def mel_grid(sample_rate, num_filt, fft_len):
     """Filter edge indices: mel-uniform between 0 Hz and *sample_rate* (not Nyquist), mapped
     with int(hz * fft_len / sample_rate) where fft_len = n_fft/2+1 (mfcc.h:230-249 as called
-    from speech_commands.h:304-307)."""
+    from speech_commands.h:304-307).
+
+    Repeated indices are kept (the filters between them are empty and give log(eps)).  sonopy has a
+    ``correct_grid`` helper meant to push duplicates forward, but as published it is a no-op: it is
+    handed an ndarray, so ``[x[0] - 1] + x`` broadcasts to ``x - 1`` and its offset never leaves 0.
+    The reference's own C++ twin has no such step either; tests/golden/ref_mfcc_cpp.npz pins a
+    duplicate-grid case (n_fft 512, 40 filters) against it."""
     mels = np.linspace(hertz_to_mels(0.0), hertz_to_mels(float(sample_rate)), num_filt + 2, True)
     hz = mels_to_hertz(mels)
     idx = (hz * fft_len / sample_rate).astype(int)
-    return _dedup_forward([int(i) for i in idx])
+    return [int(i) for i in idx]
 
 
 @lru_cache(maxsize=None)

@@ -99,6 +99,10 @@ def main():
     cpp['mfcc_params_json'] = np.stack([cpp_mfcc(lib, a, 16000, 1024, 512, 1024, 20, 20) for a in audio])
     cpp['mfcc_params_json_synth'] = np.stack([cpp_mfcc(lib, a, 16000, 1024, 512, 1024, 20, 20) for a in synth_f])
     cpp['mfcc_512_256_512_20_13'] = np.stack([cpp_mfcc(lib, a, 16000, 512, 256, 512, 13, 20) for a in audio[:2]])
+    # a mel grid with repeated points (n_fft 512, 40 filters: empty filters -> log(eps)); the twin has no de-duplication
+    cpp['mfcc_512_256_512_40_13_dupgrid'] = np.stack([cpp_mfcc(lib, a, 16000, 512, 256, 512, 13, 40) for a in audio[:2]])
+    # ... and one whose first filter is empty altogether (n_fft 256, 40 filters: grid 0, 0, 0, 1, 2, 2, ...)
+    cpp['mfcc_256_128_256_40_13_dupgrid'] = np.stack([cpp_mfcc(lib, a, 16000, 256, 128, 256, 13, 40) for a in audio[:2]])
     cpp['mfcc_preproc'] = np.stack([cpp_mfcc(lib, a, 16000, 1024, 512, 1024, 20, 20, pre=1) for a in audio[:2]])
     lib.ref_mfcc_delta.restype = ctypes.c_int
     lib.ref_mfcc_delta.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 8 + [ctypes.c_void_p]
@@ -112,6 +116,9 @@ def main():
     bank = np.zeros((40, 257))
     lib.ref_filterbanks(16000, 512, 40, 0, 16000, bank.ctypes.data)
     cpp['bank_16000_40_512'] = bank
+    bank = np.zeros((40, 129))
+    lib.ref_filterbanks(16000, 256, 40, 0, 16000, bank.ctypes.data)
+    cpp['bank_16000_40_256'] = bank
     np.savez_compressed(os.path.join(HERE, 'ref_mfcc_cpp.npz'), **cpp)
 
     # ---- oracle regression pin ------------------------------------------------------------

@@ -428,6 +428,80 @@ def test_stream_device_push_ring_copy_and_small_ring(example_pcm):
             _lib.lib().scf_stream_destroy(h)
 
 
+@pytest.mark.parametrize('n_streams,chunk,rows,steps', [(256, 1600, 30, 14), (3, 3000, 2, 10), (64, 512, 30, 24)])
+def test_stream_back_to_back_pushes_without_host_sync(n_streams, chunk, rows, steps):
+    """include/scfeat.h: pushes of one scf_stream are stream-ordered -- no host synchronisation is needed between them.
+    Every push reads the state its predecessor wrote, and consecutive launches overlap through programmatic
+    dependent launch, so the kernel has to wait for its predecessor before its first READ of stream state.  All
+    pushes are enqueued at once; each step's ring and row count go to their own device buffers and are compared
+    with the listen.py:96-114 state machine after ONE synchronisation at the end."""
+    import ctypes
+    import torch
+    from scfeat import _lib
+    p = opipe.Params()
+    rng = np.random.default_rng(31)
+    x = rng.integers(-32768, 32768, size=(n_streams, steps, chunk), dtype=np.int16)
+    plan = scfeat.get_plan()
+    h = ctypes.c_void_p()
+    _lib.check(_lib.lib().scf_stream_create(plan.handle, n_streams, rows, chunk, ctypes.byref(h)))
+    try:
+        for rep in range(3):                        # repeated: a race does not have to show on the first attempt
+            st = torch.cuda.Stream()
+            d_chunks = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2))).cuda()       # [steps][streams][chunk]
+            d_rings = torch.full((steps, n_streams, rows, 20), float('nan'), dtype=torch.float32, device='cuda')
+            d_new = torch.full((steps, n_streams), -1, dtype=torch.int32, device='cuda')
+            torch.cuda.synchronize()
+            _lib.check(_lib.lib().scf_stream_reset(h, ctypes.c_void_p(st.cuda_stream)))
+            for t in range(steps):
+                _lib.check(_lib.lib().scf_stream_push_i16(h, d_chunks[t].data_ptr(), chunk, d_rings[t].data_ptr(),
+                                                          d_new[t].data_ptr(), ctypes.c_void_p(st.cuda_stream)))
+            st.synchronize()
+            rings, new = d_rings.cpu().numpy(), d_new.cpu().numpy()
+            check = range(n_streams) if n_streams <= 64 else list(range(0, n_streams, 9)) + [n_streams - 1]
+            for i in check:
+                o = opipe.ListenerOracle(p)
+                o.mfccs = np.zeros((rows, p.n_mfcc))
+                for t in range(steps):
+                    before = len(o.window_audio)
+                    want = o.update_vectors(x[i, t].tobytes())[..., 0]
+                    k = (before + chunk - len(o.window_audio)) // p.hop_samples
+                    assert new[t, i] == k, (rep, i, t)
+                    assert np.abs(rings[t, i] - want).max() <= CEP_REL * max(np.abs(want).max(), 1.0), (rep, i, t)
+            # the row counts of ALL streams (cheap): same chunk length -> same count for every stream
+            assert (new == new[:, :1]).all()
+    finally:
+        _lib.lib().scf_stream_destroy(h)
+
+
+def test_mel_grid_with_repeated_points_vs_compiled_reference_cpp(example_pcm, ref_cpp):
+    """n_fft 512 / 256 with 40 mel filters: the grid has repeated points, some filters are one-sided or empty
+    (log(eps) = -36.04 in that band).  The reference's C++ twin (mfcc.h:230-264) keeps them; so does the kernel."""
+    _, pcm = example_pcm
+    for (w, hop, nfft), key in (((512, 256, 512), 'mfcc_512_256_512_40_13_dupgrid'),
+                                ((256, 128, 256), 'mfcc_256_128_256_40_13_dupgrid')):
+        want = ref_cpp[key]
+        got = np.stack([scfeat.sonopy.mfcc_spec(a, 16000, (w, hop), nfft, 40, 13) for a in audio_of(pcm[:2])])
+        assert_cepstrum_close(got, want)
+        orc = np.stack([osonopy.mfcc_spec(a, 16000, (w, hop), nfft, 40, 13) for a in audio_of(pcm[:2])])
+        assert_cepstrum_close(got, orc)
+    mel = scfeat.sonopy.mel_spec(audio_of(pcm[0]), 16000, (256, 128), 256, 40)
+    assert_log_close(mel, osonopy.mel_spec(audio_of(pcm[0]), 16000, (256, 128), 256, 40))
+    np.testing.assert_allclose(mel[:, 0], -36.04365339, atol=2e-5)             # filter 0 is empty
+
+
+def test_preemphasis_and_hamming_vs_compiled_reference_cpp(example_pcm, ref_cpp):
+    """The same front end pinned to the reference itself: mfcc::mfcc<float>(use_preprocess=true) compiled from
+    inference/tflite/mfcc.h:394-410 (tests/golden/ref_mfcc_cpp.npz 'mfcc_preproc').  Frame 0 is skipped: its first
+    sample reads audio_data[-1] in the reference (out of bounds); the contract here is x[-1] := 0."""
+    _, pcm = example_pcm
+    want = ref_cpp['mfcc_preproc']
+    plan = scfeat.get_plan(window=1024, hop=512, n_fft=1024, n_filt=20, n_coeffs=20, preemph_alpha=0.95, window_fn='hamming')
+    got = plan.extract_host(pcm[:2])
+    assert got.shape == want.shape == (2, 30, 20)
+    assert_cepstrum_close(got[:, 1:], want[:, 1:])
+    assert_cepstrum_close(plan.extract_host(audio_of(pcm[:2]))[:, 1:], want[:, 1:])
+
+
 def test_ragged_batch_fast_path_random_lengths(example_pcm):
     """Per-clip lengths with front padding run on the fast kernels (predicated loads only for the pair that straddles
     the padding): every possible alignment of the first valid sample inside a frame pair, int16 and float input."""

@@ -53,6 +53,13 @@ def test_mel_bank_equals_oracle(sr, nf, nfft):
 def test_mel_bank_equals_cpp_twin(ref_cpp):
     got = _lib.build_bank(sample_rate=16000, n_fft=1024, n_filt=20, bank=_lib.BANK_MEL_SONOPY)
     np.testing.assert_allclose(got, ref_cpp['bank_16000_20_1024'], rtol=1e-14, atol=0)
+    # repeated grid points are kept, as the twin does (empty / one-sided filters)
+    for n_fft, key in ((512, 'bank_16000_40_512'), (256, 'bank_16000_40_256')):
+        got = _lib.build_bank(sample_rate=16000, n_fft=n_fft, n_filt=40, bank=_lib.BANK_MEL_SONOPY)
+        want = ref_cpp[key]
+        assert np.array_equal(got != 0, want != 0)
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+    assert (want.sum(axis=1) == 0).any()           # n_fft 256: filter 0 is empty altogether
 
 
 @pytest.mark.parametrize('nf,nfft,scale', [(20, 512, 'constant'), (20, 1024, 'constant'), (24, 512, 'constant'),
@@ -81,7 +88,8 @@ def test_dct_equals_oracle(nf, nc):
     dict(n_fft=512, n_filt=26, bank=_lib.BANK_BARK_REF),                       # bfcc_spec defaults
     dict(n_fft=512, n_filt=24, bank=_lib.BANK_BARK_REF, bank_scale='ascendant'),
     dict(n_fft=512, n_filt=20, bank=_lib.BANK_MEL_SONOPY),                     # sonopy defaults
-    dict(n_fft=512, n_filt=40, bank=_lib.BANK_MEL_SONOPY),                     # repeated grid points (correct_grid)
+    dict(n_fft=512, n_filt=40, bank=_lib.BANK_MEL_SONOPY),                     # repeated grid points: empty filters
+    dict(n_fft=256, n_filt=40, bank=_lib.BANK_MEL_SONOPY),                     # ... with an empty filter
     dict(n_fft=256, n_filt=13, bank=_lib.BANK_MEL_SONOPY, sample_rate=8000),
     dict(n_fft=1024, n_filt=64, bank=_lib.BANK_MEL_SONOPY),
     dict(n_fft=1024, n_filt=64, bank=_lib.BANK_BARK_REF),

@@ -98,6 +98,19 @@ def test_mel_bank_matches_cpp_twin(ref_cpp):
     np.testing.assert_allclose(sonopy.filterbanks(16000, 20, 513), ref_cpp['bank_16000_20_1024'], rtol=1e-14, atol=0)
 
 
+def test_mel_bank_with_repeated_grid_points_matches_cpp_twin(ref_cpp):
+    # n_fft 512 / 40 filters: the raw grid starts 0, 0, 1, 2, 2, ... -- the twin (mfcc.h:230-264) keeps the repeats,
+    # so some filters are empty or one-sided; a de-duplicating restatement differs in 20 of the 40 rows
+    # (n_fft 256 / 40 filters starts 0, 0, 0, 1, 2, 2: filter 0 is empty altogether)
+    for bins, key, n_empty in ((257, 'bank_16000_40_512', 0), (129, 'bank_16000_40_256', 1)):
+        grid = sonopy.mel_grid(16000, 40, bins)
+        assert len(set(grid)) < len(grid)
+        want = ref_cpp[key]
+        got = sonopy.filterbanks(16000, 40, bins)
+        assert np.array_equal(got != 0, want != 0) and int((want.sum(axis=1) == 0).sum()) >= n_empty
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+
+
 def test_mfcc_matches_cpp_twin(example_pcm, ref_cpp, ref_bark):
     _, pcm = example_pcm
     got = np.stack([sonopy.mfcc_spec(x, 16000, (1024, 512), 1024, 20, 20) for x in audio_of(pcm)])
@@ -107,6 +120,11 @@ def test_mfcc_matches_cpp_twin(example_pcm, ref_cpp, ref_bark):
     assert np.abs(got - ref_cpp['mfcc_params_json_synth']).max() < 1e-6
     got = np.stack([sonopy.mfcc_spec(x, 16000, (512, 256), 512, 20, 13) for x in audio_of(pcm[:2])])
     assert np.abs(got - ref_cpp['mfcc_512_256_512_20_13']).max() < 1e-6
+    # repeated grid points: empty filters give log(eps) = -36.04 in both
+    got = np.stack([sonopy.mfcc_spec(x, 16000, (512, 256), 512, 40, 13) for x in audio_of(pcm[:2])])
+    assert np.abs(got - ref_cpp['mfcc_512_256_512_40_13_dupgrid']).max() < 5e-6       # |values| reach 60: fp32 output rounding
+    got = np.stack([sonopy.mfcc_spec(x, 16000, (256, 128), 256, 40, 13) for x in audio_of(pcm[:2])])
+    assert np.abs(got - ref_cpp['mfcc_256_128_256_40_13_dupgrid']).max() < 5e-6
 
 
 def test_mfcc_known_answers(example_pcm):

@@ -53,6 +53,9 @@ static std::vector<double> linspace(double start, double stop, int num)
 
 // sonopy.filterbanks(sample_rate, n_filt, fft_len) -- restated from its published algorithm; C++ twin
 // inference/tflite/mfcc.h:230-264 with low=0, high=sample_rate (speech_commands.h:304-307).
+// Repeated grid points are kept as they are (filters between them come out empty and give log(eps)): the C++ twin has
+// no de-duplication, and sonopy's own `correct_grid` helper is a no-op as published -- it is handed an ndarray, so
+// `[x[0] - 1] + x` broadcasts to x - 1 instead of prepending, and its offset never leaves 0.
 static void build_mel_sonopy(int sample_rate, int n_filt, int n_bins, std::vector<double>& bank)
 {
     auto hz2mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };      // mfcc.h:134-138
@@ -60,16 +63,6 @@ static void build_mel_sonopy(int sample_rate, int n_filt, int n_bins, std::vecto
     std::vector<double> mels = linspace(hz2mel(0.0), hz2mel((double)sample_rate), n_filt + 2);
     std::vector<long> grid(n_filt + 2);
     for (int i = 0; i < n_filt + 2; ++i) grid[i] = (long)(mel2hz(mels[i]) * (double)n_bins / (double)sample_rate);
-    // sonopy's correct_grid: push repeated points forward so that no filter is empty
-    {
-        long offset = 0, prev = grid[0] - 1;
-        for (int i = 0; i < n_filt + 2; ++i) {
-            const long cur = grid[i];
-            offset = std::max(0L, offset + prev + 1 - cur);
-            grid[i] = cur + offset;
-            prev = cur;
-        }
-    }
     bank.assign((size_t)n_filt * n_bins, 0.0);
     for (int i = 0; i < n_filt; ++i) {
         const long l = grid[i], m = grid[i + 1], r = grid[i + 2];

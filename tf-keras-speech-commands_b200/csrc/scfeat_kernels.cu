@@ -24,6 +24,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "fft_gen.cuh"
 #include "scfeat_internal.h"
 
@@ -302,7 +305,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 
     // Programmatic dependent launch: let the NEXT extract launch of the stream start filling SMs as soon as
     // this grid's CTAs retire (its loads / FFTs do not depend on us).  Every extract grid waits for its
-    // predecessor (griddepcontrol.wait below) before its first global store, so output ordering is kept;
+    // predecessor (griddepcontrol.wait below) before its first global store, so output ordering is kept -- and
+    // before its first load of anything an extract grid writes (streaming state), see below;
     // kernels launched without the attribute (everything else in the stream) still wait for full completion.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     bool deps_done = false;
@@ -312,6 +316,15 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     if (threadIdx.x == 0) {
         mbar_init(s_bar, 1);
         bulk_g2s(s_tab, p.tables, (uint32_t)staged_bytes, s_bar);
+    }
+    // A streaming step READS what its predecessor wrote (carry, carry length, ring): it must not touch any of that
+    // before the previous push has completed, so it waits here instead of before its first store.  The launch
+    // latency and the table copy above still overlap the predecessor.
+    if constexpr (!FAST && sizeof(InT) == 2) {
+        if (p.stream_on) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            deps_done = true;
+        }
     }
     // (no zero fill of the exchange area: every float of a valid pair row is rewritten each tile, and whatever an
     //  unused slot holds only reaches that slot's own, discarded, results)
@@ -905,15 +918,21 @@ template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
 {
     auto kern = extract_kernel<R, InT, FAST, TEAMS, DENSE>;
-    static size_t configured[16] = {0};          // per device: the attribute call costs microseconds per launch
+    // per device: the attribute call costs microseconds per launch, so it is made once per size (plans are shared
+    // between threads: the bookkeeping is atomic, and setting the attribute twice is harmless)
+    static std::atomic<size_t> configured[16];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (smem > configured[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (DENSE)       // ask for the largest shared-memory carve-out so that three CTAs (or the big one) fit
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured[dev & 15] = smem;
+    if (smem > configured[dev & 15].load(std::memory_order_acquire)) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured[dev & 15].load(std::memory_order_relaxed)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (DENSE)   // ask for the largest shared-memory carve-out so that three CTAs (or the big one) fit
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            configured[dev & 15].store(smem, std::memory_order_release);
+        }
     }
     const int64_t ctas_per_sm = TEAMS == 3 ? 1 : (DENSE ? 3 : kCtasPerSm);
     int64_t grid = (int64_t)num_sms * ctas_per_sm;
