@@ -183,6 +183,49 @@ int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_le
 int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chunk_len, float* h_ring_out,
                              int32_t* h_new_rows);
 
+/* ---- streaming post-processing on the device: replaces the per-chunk scalar work listen.py does after the model,
+ *      ThresholdDecoder (listen.py:452-521; C++ twin inference/tflite/threshold_decoder.h:19-113) and
+ *      TriggerDetector (listen.py:525-559; twin inference/tflite/speech_commands.h:263-289), for n_streams
+ *      concurrent listeners.  Arithmetic is float64 like the Python path. ------------------------------------ */
+typedef struct scf_post scf_post;
+
+/* ThresholdDecoder.__init__ (listen.py:466-471, 519-521), host only: min_out / max_out and the cumulative table
+ * cd = cumsum(sum_i pdf(points; mu_i, std_i) / (resolution * n_mu)), points = linspace(min_out, max_out,
+ * resolution * (max_out - min_out)).  mu_stds = n_mu (mu, std) pairs.  Call with cd_out = NULL to get the size in
+ * *n_cd; with cd_out set, *n_cd is its capacity on entry. */
+int scf_post_build_cd(const double* mu_stds, int32_t n_mu, int32_t resolution, double min_z, double max_z,
+                      int32_t* min_out, int32_t* max_out, double* cd_out, int64_t* n_cd);
+
+/* Decoder table on the device plus n_streams trigger state machines (activation = 0, record_index = None).
+ * class_is_background[c] != 0 marks the 'background' class (listen.py:544); chunk_size, sensitivity and trigger_level
+ * are TriggerDetector's constructor arguments.  device = -1: the current one. */
+int scf_post_create(const double* mu_stds, int32_t n_mu, double center, int32_t resolution, double min_z, double max_z,
+                    const uint8_t* class_is_background, int32_t n_classes, int32_t n_streams, int32_t chunk_size,
+                    double sensitivity, int32_t trigger_level, int32_t device, scf_post** post_out);
+void scf_post_destroy(scf_post* post);
+int scf_post_reset(scf_post* post, void* cuda_stream);
+
+/* Element-wise ThresholdDecoder.decode (listen.py:497-509) of n raw outputs; device pointers, stream-ordered. */
+int scf_post_decode(const scf_post* post, const double* d_raw, int64_t n, double* d_out, void* cuda_stream);
+
+/* One iteration of the listen.py loop after the model (listen.py:411-425) for every stream, ONE launch:
+ * index = argmax(probs[s]), score = max(probs[s]); a non-background score goes through decode (the float32 score's
+ * 1 / x - 1 is evaluated in float32, as numpy does for the model's output); TriggerDetector.update(index, score).
+ * d_probs: [n_streams][n_classes] float32.  Outputs (each nullable): class index, decoded score, 1 where the stream
+ * activated in this step. */
+int scf_post_step(scf_post* post, const float* d_probs, int32_t* d_index_out, double* d_score_out, uint8_t* d_fired_out,
+                  void* cuda_stream);
+
+/* TriggerDetector.update(index, score) alone (listen.py:538-559) for every stream: class indices and already decoded
+ * scores in, activation flags out; device pointers, one launch. */
+int scf_post_trigger_update(scf_post* post, const int32_t* d_index, const double* d_score, uint8_t* d_fired_out,
+                            void* cuda_stream);
+
+/* Copies the trigger state to the host (synchronises cuda_stream): activation counters and recorded class
+ * indices (-1 = None).  Either pointer may be NULL. */
+int scf_post_state(const scf_post* post, int32_t* h_activation, int32_t* h_record_index, void* cuda_stream);
+int scf_post_info(const scf_post* post, int32_t* min_out, int32_t* max_out, int64_t* n_cd);
+
 /* ---- multi-GPU feature-cache assembly (new; the reference is single-process) ------------------ */
 
 /* Fused extract + all-gather over NVLink peer memory: this rank extracts its n_local clips and the kernel

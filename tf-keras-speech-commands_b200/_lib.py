@@ -34,6 +34,8 @@ EXPORTS = [
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
     'scf_measure_fp32_flops', 'scf_device_malloc', 'scf_device_free', 'scf_memcpy', 'scf_ipc_export',
     'scf_ipc_import', 'scf_ipc_close',
+    'scf_post_build_cd', 'scf_post_create', 'scf_post_destroy', 'scf_post_reset', 'scf_post_decode', 'scf_post_step',
+    'scf_post_trigger_update', 'scf_post_state', 'scf_post_info',
 ]
 
 
@@ -122,6 +124,18 @@ def lib():
         L.scf_ipc_export.argtypes = [i32, vp, vp]
         L.scf_ipc_import.argtypes = [i32, vp, ctypes.POINTER(vp)]
         L.scf_ipc_close.argtypes = [i32, vp]
+        f64 = ctypes.c_double
+        L.scf_post_build_cd.argtypes = [vp, i32, i32, f64, f64, ctypes.POINTER(i32), ctypes.POINTER(i32), vp,
+                                        ctypes.POINTER(i64)]
+        L.scf_post_create.argtypes = [vp, i32, f64, i32, f64, f64, vp, i32, i32, i32, f64, i32, i32, ctypes.POINTER(vp)]
+        L.scf_post_destroy.argtypes = [vp]
+        L.scf_post_destroy.restype = None
+        L.scf_post_reset.argtypes = [vp, vp]
+        L.scf_post_decode.argtypes = [vp, vp, i64, vp, vp]
+        L.scf_post_step.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.scf_post_trigger_update.argtypes = [vp, vp, vp, vp, vp]
+        L.scf_post_state.argtypes = [vp, vp, vp, vp]
+        L.scf_post_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
         _lib = L
         return _lib
 

@@ -29,6 +29,8 @@ static int fail(int code, const std::string& msg)
     return code;
 }
 
+int post_fail(int code, const char* msg) { return fail(code, msg); }     // for scfeat_post.cu
+
 #define SCF_CUDA(call)                                                                              \
     do {                                                                                            \
         cudaError_t e__ = (call);                                                                   \
@@ -600,6 +602,7 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.n_filt = c.n_filt;
     kp.n_filt4 = plan->n_filt4;
     kp.n_out = plan->n_out;
+    kp.frames_odd = kp.frames_per_clip & 1;
     magic_div((uint32_t)std::max(1, kp.pairs_per_clip), kp.ppc_magic, kp.ppc_shift);
     const int ppt = pairs_per_tile(plan->radix_r);
     n_tiles = (kp.n_pairs + ppt - 1) / ppt;

@@ -360,9 +360,25 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     const uint32_t n_pairs = (uint32_t)p.n_pairs;
     bool tables_ready = false;
 
+    // ---- where this warp is: its first pair of the current tile as (clip, pair inside the clip), advanced by a fixed
+    //      (clips, pairs) step per tile -- one division per kernel instead of three per pair
     const uint32_t tile_stride = gridDim.x * TEAMS;
     const uint32_t tile_first = blockIdx.x * TEAMS + team;
-    // (clip, pair inside the clip) of global pair gp
+    const uint32_t step_pairs = tile_stride * geo::PPT;
+    const uint32_t step_c = fast_div(step_pairs, p.ppc_magic, p.ppc_shift);
+    const uint32_t step_q = step_pairs - step_c * ppc;
+    uint32_t gp0 = tile_first * geo::PPT + warp * geo::G;
+    uint32_t clip0 = fast_div(gp0, p.ppc_magic, p.ppc_shift);
+    uint32_t q0 = gp0 - clip0 * ppc;
+    // position of pair g of the warp, given the position of its pair 0
+    auto pair_of = [&](uint32_t c_in, uint32_t q_in, int g, uint32_t& c_out, uint32_t& q_out) {
+        c_out = c_in;
+        q_out = q_in + g;
+        if constexpr (geo::G > 1) {
+            while (q_out >= ppc) { q_out -= ppc; ++c_out; }
+        }
+    };
+    // (clip, pair inside the clip) of an arbitrary global pair (streaming epilogue only)
     auto pair_pos = [&](uint32_t gp, uint32_t& c_out, uint32_t& q_out) {
         c_out = fast_div(gp, p.ppc_magic, p.ppc_shift);
         q_out = gp - c_out * ppc;
@@ -380,8 +396,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         if (p.lengths != nullptr) pad = p.clip_len - min(max(__ldg(p.lengths + clip), 0), p.clip_len);
         const int e0 = (int)q * geo::NFFT;                    // first element of the pair in the padded clip
         const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
-        const int n_ld = ((int)(2 * q + 1) < p.frames_per_clip) ? geo::NLOAD : R;
-        if (__builtin_expect(pad <= e0 && n_ld == geo::NLOAD, 1)) {
+        const bool b_absent = p.frames_odd != 0 && q + 1 == ppc;
+        const int n_ld = b_absent ? R : geo::NLOAD;
+        if (__builtin_expect(pad <= e0 && !b_absent, 1)) {
             const InT* __restrict__ src = cb + (e0 - pad) + lane;
 #pragma unroll
             for (int j = 0; j < geo::NLOAD; ++j) dst[j] = ld_sample(src + 32 * j);
@@ -397,27 +414,31 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead;
     //  the 24-warp CTAs have no registers to spare and prefetch into L2 instead)
     constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;
-    auto prefetch = [&](uint32_t tile) {
+    auto prefetch = [&](uint32_t gp, uint32_t c_in, uint32_t q_in) {
         if constexpr (kPrefetch) {
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
-                const uint32_t gp = tile * geo::PPT + warp * geo::G + g;
-                if (gp < n_pairs) {
+                if (gp + g < n_pairs) {
                     uint32_t clip, q;
-                    pair_pos(gp, clip, q);
+                    pair_of(c_in, q_in, g, clip, q);
                     load_pair(clip, q, raw[g]);
                 }
             }
         }
     };
-    if (tile_first < n_tiles) prefetch(tile_first);
+    if (tile_first < n_tiles) prefetch(gp0, clip0, q0);
     __syncthreads();          // mbarrier init + zeroed s_logq pad rows visible (the only CTA-wide barrier)
 
     for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
         const uint32_t pair0 = tile * geo::PPT;
+        // where this warp will be in its next tile: used for the prefetch now, and as the position then
+        const uint32_t gp_n = gp0 + step_pairs;
+        uint32_t clip_n = clip0 + step_c, q_n = q0 + step_q;
+        if (q_n >= ppc) { q_n -= ppc; ++clip_n; }
+        const bool more = tile + tile_stride < n_tiles;
 
         // =========================== FFT stage (per warp) =======================================
-        if (pair0 + warp * geo::G < n_pairs) {
+        if (gp0 < n_pairs) {
             // ---- pass 1: lane = n2; R-point FFT over n1 of z[n2 + 32 n1], z = A + iB ----------------
             // A frame whose samples are ALL exactly zero (front padding, digital silence) must come out as exactly
             // zero power: the two-for-one separation below would otherwise leak ~4e-15 of its partner's energy into
@@ -425,26 +446,25 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             uint32_t zero_mask = 0;
 #pragma unroll
             for (int g = 0; g < geo::G; ++g) {
-                const uint32_t gp = pair0 + warp * geo::G + g;
-                if (gp < n_pairs) {
+                if (gp0 + g < n_pairs) {
                     uint32_t clip, q;
-                    pair_pos(gp, clip, q);
+                    pair_of(clip0, q0, g, clip, q);
                     f2 x[R];                                   // (re, im) = (frame A sample, frame B sample), packed
                     uint32_t nz_a = 0, nz_b = 0;
                     int n_frames = p.frames_per_clip;          // rows this clip produces
                     if constexpr (FAST) {
+                        const bool b_absent = p.frames_odd != 0 && q + 1 == ppc;          // odd frame count: last pair
                         if constexpr (!kPrefetch) {
                             load_pair(clip, q, raw[g]);
                             // pull the samples this warp needs in its NEXT tile into L2 (one 128-byte line per lane)
-                            if (gp + tile_stride * geo::PPT < n_pairs) {
+                            if (gp_n + g < n_pairs) {
                                 uint32_t clipn, qn;
-                                pair_pos(gp + tile_stride * geo::PPT, clipn, qn);
+                                pair_of(clip_n, q_n, g, clipn, qn);
                                 const InT* nsrc = in + (int64_t)clipn * p.clip_stride + qn * geo::NFFT;
                                 if (lane * 128 < (int)(geo::NLOAD * 32 * sizeof(InT)) + 128)
                                     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(nsrc) + lane * 128));
                             }
                         }
-                        const bool b_absent = (int)(2 * q + 1) >= p.frames_per_clip;      // odd frame count: last pair
                         if (bit_detect) {
                             uint32_t o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
@@ -553,7 +573,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             // lane's own register 32 - k2): a fixed lane permutation, done with shuffles -- one SHFL moves what takes
             // an STS plus an LDS wavefront through shared memory (tools/microbench/shfl_vs_lds.cu: 33 vs 65 cycles).
             // the loads of the next tile's samples are issued here: they fill the wait for the mirror values
-            if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
+            if (more) prefetch(gp_n, clip_n, q_n);
             float* prow = pw + g2 * geo::PROW2;
             const int src_lane = (lane & ~(R - 1)) | ((R - k1) & (R - 1));
             f2 esum = pk(0.f, 0.f);
@@ -597,8 +617,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 tables_ready = true;
             }
             if (lane < geo::G) s_info[warp * geo::G + lane].y = ~0ull;          // no pair, no rows
-            if (tile + tile_stride < n_tiles) prefetch(tile + tile_stride);
+            if (more) prefetch(gp_n, clip_n, q_n);
         }
+        gp0 = gp_n;
+        clip0 = clip_n;
+        q0 = q_n;
         if (!deps_done) {         // before this grid's first global store
             asm volatile("griddepcontrol.wait;" ::: "memory");
             deps_done = true;

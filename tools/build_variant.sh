@@ -11,5 +11,6 @@ mkdir -p $out /tmp/scf_$name
 F="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -I$root/include -I$src $extra"
 nvcc $F -c $src/scfeat_kernels.cu -o /tmp/scf_$name/k.o
 nvcc $F -c $src/scfeat_host.cu -o /tmp/scf_$name/h.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libscfeat_$name.so /tmp/scf_$name/k.o /tmp/scf_$name/h.o -ldl
+nvcc $F -c $src/scfeat_post.cu -o /tmp/scf_$name/p.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libscfeat_$name.so /tmp/scf_$name/k.o /tmp/scf_$name/h.o /tmp/scf_$name/p.o -ldl
 echo $out/libscfeat_$name.so
