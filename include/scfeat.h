@@ -67,6 +67,14 @@ typedef enum scf_window_kind { SCF_WIN_RECT = 0, SCF_WIN_HAMMING = 1, SCF_WIN_HA
  *                      clip's own length are produced; the remaining rows are left untouched. */
 typedef enum scf_pad_kind { SCF_PAD_FRONT_ZERO = 0, SCF_PAD_NONE = 1 } scf_pad_kind;
 
+/* Delta features appended to every output row (on the frame axis of each clip), computed on the device right after
+ * the extraction:
+ * SCF_DELTA_DIFF     : add_deltas, common/data_utils.py:50-58 -- d[i] = f[i] - f[i-1], d[0] = 0     -> 2x columns
+ * SCF_DELTA_CENTRAL  : mfcc::mfcc(use_delta), inference/tflite/mfcc.h:432-441 -- (f[i+1] - f[i-1]) / 2 with the edges
+ *                      clamped                                                                        -> 2x columns
+ * SCF_DELTA_CENTRAL2 : ... plus use_delta2, mfcc.h:443-453: the same difference of the delta columns  -> 3x columns */
+typedef enum scf_delta_kind { SCF_DELTA_NONE = 0, SCF_DELTA_DIFF = 1, SCF_DELTA_CENTRAL = 2, SCF_DELTA_CENTRAL2 = 3 } scf_delta_kind;
+
 typedef struct scf_config {
     int32_t sample_rate;     /* classifier/params.py:52                    default 16000 */
     int32_t window;          /* window_samples, classifier/params.py:70-73 default 1024  */
@@ -81,7 +89,7 @@ typedef struct scf_config {
     float   preemph_alpha;   /* 0 = off; mfcc.h:396 uses 0.95; x[-1] := 0                */
     float   pcm_scale;       /* int16 -> float factor, 1/32768 (common/data_utils.py:21); ignored for float input */
     int32_t device;          /* CUDA device ordinal, -1 = current                        */
-    int32_t reserved;
+    int32_t delta;           /* scf_delta_kind (pr.use_delta -> SCF_DELTA_DIFF)          default NONE  */
     const double* custom_bank; /* SCF_BANK_CUSTOM only                                   */
 } scf_config;
 
@@ -96,7 +104,7 @@ int scf_config_default(scf_config* cfg);
 /* Number of frames chop_array yields for n_samples (common/bark_feature.py:80-82). */
 int64_t scf_num_frames(int64_t n_samples, int32_t window, int32_t hop);
 
-/* Output columns for this configuration (see scf_output_kind). */
+/* Output columns for this configuration (see scf_output_kind), delta columns included. */
 int32_t scf_out_cols(const scf_config* cfg);
 
 /* Dense float64 filterbank [n_filt][n_fft/2+1] exactly as the reference builds it. */

@@ -502,6 +502,72 @@ def test_preemphasis_and_hamming_vs_compiled_reference_cpp(example_pcm, ref_cpp)
     assert_cepstrum_close(plan.extract_host(audio_of(pcm[:2]))[:, 1:], want[:, 1:])
 
 
+# ------------------------------------------------------------------ delta features on the device
+def test_delta_features_on_device(example_pcm, ref_cpp):
+    """scf_config.delta: 'diff' = add_deltas (common/data_utils.py:50-58), 'central' = mfcc::mfcc(use_delta)
+    (inference/tflite/mfcc.h:432-441, pinned to the compiled twin's output), 'central2' = ... plus use_delta2
+    (mfcc.h:443-453).  The delta columns are exact functions of the float32 base columns the same call returns."""
+    _, pcm = example_pcm
+    base = scfeat.get_plan().extract_host(pcm)                                   # [8, 30, 20]
+    diff = scfeat.get_plan(delta='diff').extract_host(pcm)
+    assert diff.shape == (8, 30, 40)
+    assert np.array_equal(diff[..., :20], base)
+    want = np.zeros_like(base)
+    want[:, 1:] = base[:, 1:] - base[:, :-1]
+    assert np.array_equal(diff[..., 20:], want)
+    for i in range(8):                                                           # ... and equal the oracle's add_deltas
+        o = opipe.add_deltas(osonopy.mfcc_spec(audio_of(pcm[i]), 16000, (1024, 512), 1024, 20, 20))
+        assert_cepstrum_close(diff[i], o)
+    cen = scfeat.get_plan(delta='central').extract_host(pcm)
+    nxt, prv = np.minimum(np.arange(30) + 1, 29), np.maximum(np.arange(30) - 1, 0)
+    d1 = (base[:, nxt] - base[:, prv]) / 2
+    assert cen.shape == (8, 30, 40) and np.array_equal(cen[..., :20], base) and np.array_equal(cen[..., 20:], d1)
+    assert_cepstrum_close(cen[0], ref_cpp['mfcc_central_delta'])                 # the reference's own C++ output
+    cen2 = scfeat.get_plan(delta='central2').extract_host(pcm)
+    assert cen2.shape == (8, 30, 60) and np.array_equal(cen2[..., :40], cen)
+    assert np.array_equal(cen2[..., 40:], (d1[:, nxt] - d1[:, prv]) / 2)
+    # log-bank output, ragged clips without padding (rows of short clips stay zero), float input
+    plan = scfeat.get_plan(output=scfeat.plan.OUT_LOG_BANK, delta='central')
+    lengths = np.array([16000, 9000, 1024, 1023, 5000, 16000, 2048, 1536], dtype=np.int32)
+    got = plan.extract_host(audio_of(pcm), lengths=lengths, pad=scfeat.plan.PAD_NONE)
+    ref = scfeat.get_plan(output=scfeat.plan.OUT_LOG_BANK).extract_host(audio_of(pcm), lengths=lengths, pad=scfeat.plan.PAD_NONE)
+    for i, n in enumerate(lengths):
+        k = (n - 1024) // 512 + 1 if n >= 1024 else 0
+        assert np.array_equal(got[i, :k, :20], ref[i, :k]) and not got[i, k:].any()
+        if k:
+            nx, pv = np.minimum(np.arange(k) + 1, k - 1), np.maximum(np.arange(k) - 1, 0)
+            assert np.array_equal(got[i, :k, 20:], (ref[i, nx] - ref[i, pv]) / 2)
+    with pytest.raises(scfeat.ScfError):
+        scfeat.get_plan(output=scfeat.plan.OUT_POWER, delta='diff')
+
+
+def test_stream_with_use_delta_returns_fresh_wide_rings(example_pcm):
+    """Listener with pr.use_delta: the returned ring carries delta columns computed from its own base columns (the
+    reference re-applies add_deltas to the widened ring every chunk, listen.py:111-112 -- not copied), and every call
+    returns a fresh array (listen.py:96-114 builds a new one each time)."""
+    _, pcm = example_pcm
+    pr = scfeat.params.pr
+    try:
+        pr.__dict__.update(use_delta=True)
+        one = scfeat.listener.Listener()
+        o = opipe.ListenerOracle(opipe.Params())
+        outs = []
+        for s in range(0, 16000 - 1600 + 1, 1600):
+            got = one.update_vectors(pcm[1, s:s + 1600].tobytes())
+            base = o.update_vectors(pcm[1, s:s + 1600].tobytes())[..., 0]
+            want = opipe.add_deltas(base)
+            assert got.shape == (30, 40, 1)
+            assert np.abs(got[..., 0] - want).max() <= CEP_REL * max(np.abs(want).max(), 1.0)
+            outs.append(got)
+        assert not np.array_equal(outs[-1], outs[-2]) and outs[0] is not outs[1]          # no aliasing between calls
+    finally:
+        pr.__dict__.update(use_delta=False)
+    # empty audio: front-padded to max_samples like any short clip (common/data_utils.py:79-80) -> all-silence rows
+    z = scfeat.data_utils.audio_to_feature(np.zeros(0, dtype=np.float32))
+    assert z.shape == (30, 20)
+    np.testing.assert_allclose(z[:, 0], -36.04365339, atol=2e-5)
+
+
 def test_ragged_batch_fast_path_random_lengths(example_pcm):
     """Per-clip lengths with front padding run on the fast kernels (predicated loads only for the pair that straddles
     the padding): every possible alignment of the first valid sample inside a frame pair, int16 and float input."""

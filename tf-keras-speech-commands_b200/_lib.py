@@ -22,6 +22,7 @@ SCALE = {'constant': 0, 'ascendant': 1, 'descendant': 2}
 OUT_POWER, OUT_LOG_BANK, OUT_CEPSTRUM = 0, 1, 2
 WIN = {'rect': 0, 'hamming': 1, 'hann': 2}
 PAD_FRONT_ZERO, PAD_NONE = 0, 1
+DELTA = {None: 0, 'none': 0, 'diff': 1, 'central': 2, 'central2': 3}
 
 EXPORTS = [
     'scf_config_default', 'scf_num_frames', 'scf_out_cols', 'scf_build_bank', 'scf_build_dct',
@@ -53,7 +54,7 @@ class Config(ctypes.Structure):
         ('n_fft', ctypes.c_int32), ('n_filt', ctypes.c_int32), ('n_coeffs', ctypes.c_int32),
         ('bank', ctypes.c_int32), ('bank_scale', ctypes.c_int32), ('output', ctypes.c_int32),
         ('window_fn', ctypes.c_int32), ('preemph_alpha', ctypes.c_float), ('pcm_scale', ctypes.c_float),
-        ('device', ctypes.c_int32), ('reserved', ctypes.c_int32), ('custom_bank', ctypes.c_void_p),
+        ('device', ctypes.c_int32), ('delta', ctypes.c_int32), ('custom_bank', ctypes.c_void_p),
     ]
 
 
@@ -147,13 +148,14 @@ def check(rc):
 
 def make_config(sample_rate=16000, window=1024, hop=512, n_fft=1024, n_filt=20, n_coeffs=20,
                 bank=BANK_MEL_SONOPY, bank_scale='constant', output=OUT_CEPSTRUM, window_fn='rect',
-                preemph_alpha=0.0, pcm_scale=1.0 / 32768.0, device=-1, custom_bank=None):
+                preemph_alpha=0.0, pcm_scale=1.0 / 32768.0, device=-1, custom_bank=None, delta=None):
     c = Config()
     check(lib().scf_config_default(ctypes.byref(c)))
     c.sample_rate, c.window, c.hop, c.n_fft = int(sample_rate), int(window), int(hop), int(n_fft)
     c.n_filt, c.n_coeffs = int(n_filt), int(n_coeffs)
     c.bank, c.bank_scale, c.output = int(bank), SCALE[bank_scale], int(output)
     c.window_fn, c.preemph_alpha, c.pcm_scale, c.device = WIN[window_fn], float(preemph_alpha), float(pcm_scale), int(device)
+    c.delta = DELTA[delta]
     keep = None
     if custom_bank is not None:
         keep = np.ascontiguousarray(custom_bank, dtype=np.float64)

@@ -124,6 +124,8 @@ static int check_config(const scf_config* c)
     }
     if (c->output == SCF_OUT_CEPSTRUM && c->n_coeffs < 1) return fail(SCF_ERR_INVALID, "n_coeffs must be positive");
     if (c->window_fn < SCF_WIN_RECT || c->window_fn > SCF_WIN_HANN) return fail(SCF_ERR_INVALID, "bad window kind");
+    if (c->delta < SCF_DELTA_NONE || c->delta > SCF_DELTA_CENTRAL2) return fail(SCF_ERR_INVALID, "bad delta kind");
+    if (c->delta != SCF_DELTA_NONE && c->output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "delta features need a bank or cepstrum output");
     return SCF_OK;
 }
 
@@ -183,7 +185,8 @@ struct scf_plan {
     int num_sms = 0;
     int radix_r = 32;
     int n_bins = 0;
-    int out_cols = 0;
+    int base_cols = 0;          // columns the extract kernel produces
+    int out_cols = 0;           // columns of an output row: base_cols * (1 + delta blocks)
     float power_scale_i16 = 0.f, power_scale_f32 = 0.f;
     // device tables: the blob the kernel copies into shared memory (one per input scale), window table
     float* d_win = nullptr;
@@ -199,7 +202,8 @@ struct scf_stream {
     // double-buffered state: a push reads set `cur` and writes the other one (scfeat_internal.h StreamStep)
     int16_t* carry[2] = {nullptr, nullptr};     // [n_streams][carry_cap]
     int32_t* carry_len[2] = {nullptr, nullptr}; // [n_streams]
-    float* ring[2] = {nullptr, nullptr};        // [n_streams][ring_rows][cols]
+    float* ring[2] = {nullptr, nullptr};        // [n_streams][ring_rows][cols] (base columns: the state carries no deltas)
+    float* ring_wide = nullptr;                 // delta plans: the host push's [n_streams][ring_rows][out_cols] copy
     int32_t* n_new = nullptr;                   // [n_streams]
     int cur = 0;
     int32_t n_streams = 0, carry_cap = 0, ring_rows = 0, cols = 0;
@@ -465,6 +469,7 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     p->radix_r = cfg->n_fft / 32;
     p->n_bins = cfg->n_fft / 2 + 1;
     p->out_cols = scf_out_cols(cfg);
+    p->base_cols = p->out_cols / (cfg->delta == SCF_DELTA_NONE ? 1 : cfg->delta == SCF_DELTA_CENTRAL2 ? 3 : 2);
     const double pcm = (cfg->pcm_scale > 0.f) ? (double)cfg->pcm_scale : 1.0 / 32768.0;
     // the FFT stage leaves 2*X[k]; power_spec divides by n_fft (bark_feature.py:89)
     const double ps_f32 = 1.0 / (4.0 * cfg->n_fft);
@@ -582,7 +587,8 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     kp.out = d_out;
     kp.n_peers = 0;
     kp.peer_row0 = 0;
-    kp.out_cols = plan->out_cols;
+    kp.out_cols = plan->base_cols;
+    kp.out_pitch = plan->out_cols;
     kp.out_kind = c.output;
     kp.power_scale = is_f32 ? plan->power_scale_f32 : plan->power_scale_i16;
     {   // smallest non-zero int16 frame: one sample of +-1 -> energy 513/1024 * pcm_scale^2
@@ -612,6 +618,9 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     return SCF_OK;
 }
 
+static inline int c_window(const scf_plan* plan) { return plan->cfg.window; }
+static inline int c_hop(const scf_plan* plan) { return plan->cfg.hop; }
+
 static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out,
                           float* const* peers, int world, int rank, void* cuda_stream, int64_t clips_per_rank = 0,
@@ -626,12 +635,14 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
     if (stream_step) {
         kp.stream_on = 1;
         kp.stream = *stream_step;
+        kp.out_pitch = plan->base_cols;       // `out` is the stream's own ring: base columns only
         fast = false;             // the generic loader reads concat(carry, chunk)
     }
     kp.fast_path = fast ? 1 : 0;
     if (peers) {
         if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(SCF_ERR_INVALID, "bad world/rank");
         if (plan->cfg.output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "fused gather does not support power output");
+        if (plan->cfg.delta != SCF_DELTA_NONE) return fail(SCF_ERR_INVALID, "fused gather does not support delta features");
         kp.out = nullptr;
         kp.n_peers = world;
         for (int r = 0; r < world; ++r) {
@@ -659,11 +670,24 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
         k.in = static_cast<const unsigned char*>(d_in) + (size_t)c0 * clip_stride * esz;
         if (d_lengths) k.lengths = d_lengths + c0;
         const int64_t row0 = c0 * kp.frames_per_clip;
-        if (k.out) k.out = d_out + row0 * kp.out_cols;
+        if (k.out) k.out = d_out + row0 * kp.out_pitch;
         k.peer_row0 = kp.peer_row0 + row0;
         k.n_pairs = nc * (int64_t)kp.pairs_per_clip;
         const int64_t tiles = (k.n_pairs + ppt - 1) / ppt;
         SCF_CUDA(launch_extract(plan->radix_r, is_f32, fast, k, tiles, plan->num_sms, (cudaStream_t)cuda_stream, smem));
+    }
+    // delta columns: a second, tiny pass over the finished rows (it needs the neighbouring frames of every row, which
+    // other CTAs produced).  Launched without the programmatic attribute, so it starts after the extraction has
+    // completed, and the next extraction after it.
+    if (plan->cfg.delta != SCF_DELTA_NONE) {
+        if (stream_step) {
+            if (stream_step->ring_copy)
+                SCF_CUDA(launch_delta(stream_step->ring_copy, nullptr, n_clips, stream_step->ring_rows, plan->base_cols,
+                                      stream_step->copy_pitch, plan->cfg.delta, 0, 1, 1, SCF_PAD_FRONT_ZERO, (cudaStream_t)cuda_stream));
+        } else if (d_out) {
+            SCF_CUDA(launch_delta(d_out, d_lengths, n_clips, kp.frames_per_clip, plan->base_cols, plan->out_cols, plan->cfg.delta,
+                                  clip_len, c_window(plan), c_hop(plan), pad, (cudaStream_t)cuda_stream));
+        }
     }
     return SCF_OK;
 }
@@ -846,10 +870,11 @@ int64_t scf_num_frames(int64_t n_samples, int32_t window, int32_t hop)
 int32_t scf_out_cols(const scf_config* cfg)
 {
     if (!cfg) return 0;
+    const int blocks = cfg->delta == SCF_DELTA_NONE ? 1 : cfg->delta == SCF_DELTA_CENTRAL2 ? 3 : 2;
     switch (cfg->output) {
         case SCF_OUT_POWER: return cfg->n_fft / 2 + 1;
-        case SCF_OUT_LOG_BANK: return cfg->n_filt;
-        default: return std::min(cfg->n_filt, cfg->n_coeffs);
+        case SCF_OUT_LOG_BANK: return cfg->n_filt * blocks;
+        default: return std::min(cfg->n_filt, cfg->n_coeffs) * blocks;
     }
 }
 
@@ -1134,7 +1159,7 @@ int scf_stream_create(const scf_plan* plan, int32_t n_streams, int32_t ring_rows
     s->max_chunk = max_chunk;
     s->n_streams = n_streams;
     s->ring_rows = ring_rows;
-    s->cols = plan->out_cols;
+    s->cols = plan->base_cols;
     // carry < window before a push (listen.py:106 leaves len - k*hop < window), so window-1+max_chunk bounds it
     s->carry_cap = ((plan->cfg.window - 1 + max_chunk) + 7) & ~7;
     cudaError_t e = cudaSuccess;
@@ -1143,6 +1168,8 @@ int scf_stream_create(const scf_plan* plan, int32_t n_streams, int32_t ring_rows
         if ((e = cudaMalloc((void**)&s->carry_len[i], (size_t)n_streams * 4)) != cudaSuccess) break;
         e = cudaMalloc((void**)&s->ring[i], (size_t)n_streams * ring_rows * s->cols * 4);
     }
+    if (e == cudaSuccess && plan->cfg.delta != SCF_DELTA_NONE)
+        e = cudaMalloc((void**)&s->ring_wide, (size_t)n_streams * ring_rows * plan->out_cols * 4);
     if (e != cudaSuccess || (e = cudaMalloc((void**)&s->n_new, (size_t)n_streams * 4)) != cudaSuccess ||
         (e = cudaMalloc((void**)&s->d_chunk_stage, (size_t)n_streams * max_chunk * 2)) != cudaSuccess) {
         scf_stream_destroy(s);
@@ -1160,6 +1187,7 @@ void scf_stream_destroy(scf_stream* s)
     if (!s) return;
     DeviceGuard guard(s->plan->device);
     for (int i = 0; i < 2; ++i) { cudaFree(s->carry[i]); cudaFree(s->carry_len[i]); cudaFree(s->ring[i]); }
+    cudaFree(s->ring_wide);
     cudaFree(s->n_new);
     cudaFree(s->d_chunk_stage);
     delete s;
@@ -1197,6 +1225,7 @@ int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_le
     ss.ring_in = s->ring[in];
     ss.ring_out = s->ring[out];
     ss.ring_copy = d_ring_out;
+    ss.copy_pitch = plan->out_cols;
     ss.n_new = s->n_new;
     ss.n_new_copy = d_new_rows;
     ss.ring_rows = s->ring_rows;
@@ -1214,11 +1243,15 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
     if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
     DeviceGuard guard(s->plan->device);
     SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)s->n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
-    int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, nullptr, nullptr, nullptr);
+    // delta plans hand out wide rows: the step writes them (and their delta columns) into the stream's wide copy
+    float* wide = (h_ring_out && s->ring_wide) ? s->ring_wide : nullptr;
+    int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, wide, nullptr, nullptr);
     if (rc) return rc;
-    if (h_ring_out)         // the new ring is the state buffer the push just wrote
-        SCF_CUDA(cudaMemcpyAsync(h_ring_out, s->ring[s->cur], (size_t)s->n_streams * s->ring_rows * s->cols * 4,
+    if (h_ring_out) {       // the new ring is the state buffer the push just wrote (or its wide copy)
+        const float* src = wide ? wide : s->ring[s->cur];
+        SCF_CUDA(cudaMemcpyAsync(h_ring_out, src, (size_t)s->n_streams * s->ring_rows * s->plan->out_cols * 4,
                                  cudaMemcpyDeviceToHost, nullptr));
+    }
     if (h_new_rows)
         SCF_CUDA(cudaMemcpyAsync(h_new_rows, s->n_new, (size_t)s->n_streams * 4, cudaMemcpyDeviceToHost, nullptr));
     SCF_CUDA(cudaStreamSynchronize(nullptr));

@@ -60,6 +60,7 @@ struct StreamStep {
     const float* ring_in;        // [n_streams][ring_rows][cols]                (`mfccs` before the push)
     float* ring_out;             //                                             (listen.py:107-109)
     float* ring_copy;            // nullable: the caller's copy of the new ring
+    int32_t copy_pitch;          // floats per row of ring_copy (> cols when delta columns follow)
     int32_t* n_new;              // [n_streams] frames emitted by this step
     int32_t* n_new_copy;         // nullable
     int32_t ring_rows;
@@ -83,7 +84,8 @@ struct KParams {
     float* peer_out[kMaxPeers];  // fused all-gather targets
     int32_t n_peers;             // 0 = plain
     int64_t peer_row0;           // first output row of this rank inside the gathered cache
-    int32_t out_cols;
+    int32_t out_cols;            // columns the kernel produces per row
+    int32_t out_pitch;           // floats between rows of `out` (> out_cols when delta columns follow)
     int32_t out_kind;            // scf_output_kind
     float power_scale;           // pcm_scale^2 / (4 * n_fft) (the FFT stage leaves a factor 2)
     float zero_energy;           // int16 input: frame energies below this mean "every sample was zero"
@@ -114,6 +116,10 @@ int pairs_per_tile(int radix_r);
 int bank_groups(int radix_r);
 
 cudaError_t launch_fp32_probe(float* out, int iters, int grid, cudaStream_t st);
+// delta columns over the frame axis of finished rows, in place (scf_delta_kind); lengths / geometry give the number of
+// rows each clip really has under SCF_PAD_NONE
+cudaError_t launch_delta(float* rows, const int32_t* lengths, int64_t n_clips, int frames_per_clip, int cols, int pitch,
+                         int kind, int clip_len, int window, int hop, int pad_mode, cudaStream_t st);
 
 void count_launch(int n);
 

@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 const bool silent = kEnergyZero && ((s & 1) ? hi(e2) : lo(e2)) < p.zero_energy;
                 const int sw = (s >> 1) / geo::G;
                 const float* src = s_xch + sw * geo::XWARP + 4 * ((geo::G * sw) & 7) + ((s >> 1) % geo::G) * geo::PROW2 + (s & 1);
-                float* dst = p.out + row * p.out_cols;
+                float* dst = p.out + row * p.out_pitch;
                 for (int k = lane; k <= geo::NB; k += 32) dst[k] = silent ? 0.f : src[2 * k] * p.power_scale;
             }
             team_sync();
@@ -727,12 +727,12 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     s_stage[(2 * slot) * p.out_cols + q] = la;
                     s_stage[(2 * slot + 1) * p.out_cols + q] = lb;
                 } else {
-                    if (has_a) p.out[row_a * p.out_cols + q] = la;
-                    if (has_b) p.out[(row_a + 1) * p.out_cols + q] = lb;
+                    if (has_a) p.out[row_a * p.out_pitch + q] = la;
+                    if (has_b) p.out[(row_a + 1) * p.out_pitch + q] = lb;
                     if constexpr (!FAST) {
                         if (p.stream_on && p.stream.ring_copy != nullptr) {
-                            if (has_a) p.stream.ring_copy[row_a * p.out_cols + q] = la;
-                            if (has_b) p.stream.ring_copy[(row_a + 1) * p.out_cols + q] = lb;
+                            if (has_a) p.stream.ring_copy[row_a * p.stream.copy_pitch + q] = la;
+                            if (has_b) p.stream.ring_copy[(row_a + 1) * p.stream.copy_pitch + q] = lb;
                         }
                     }
                 }
@@ -814,9 +814,13 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                         for (int u = 0; u < 8; ++u) v[u] = j0 + 32 * u < n_old ? __ldg(ss.ring_in + r0 + kk * cols + j0 + 32 * u) : 0.f;
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            if (j0 + 32 * u < n_old) {
-                                ss.ring_out[r0 + j0 + 32 * u] = v[u];
-                                if (ss.ring_copy != nullptr) ss.ring_copy[r0 + j0 + 32 * u] = v[u];
+                            const int j = j0 + 32 * u;
+                            if (j < n_old) {
+                                ss.ring_out[r0 + j] = v[u];
+                                if (ss.ring_copy != nullptr) {
+                                    const int rr = j / cols;
+                                    ss.ring_copy[((int64_t)clip * ss.ring_rows + rr) * ss.copy_pitch + (j - rr * cols)] = v[u];
+                                }
                             }
                         }
                     }
@@ -859,14 +863,14 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 s_stage[(2 * slot) * p.out_cols + c] = lo(v);
                 s_stage[(2 * slot + 1) * p.out_cols + c] = hi(v);
             } else {
-                float* o = p.out + row_a * p.out_cols + c;
+                float* o = p.out + row_a * p.out_pitch + c;
                 if (has_a) o[0] = lo(v);
-                if (has_b) o[p.out_cols] = hi(v);
+                if (has_b) o[p.out_pitch] = hi(v);
                 if constexpr (!FAST) {
                     if (p.stream_on && p.stream.ring_copy != nullptr) {
-                        float* o2 = p.stream.ring_copy + row_a * p.out_cols + c;
+                        float* o2 = p.stream.ring_copy + row_a * p.stream.copy_pitch + c;
                         if (has_a) o2[0] = lo(v);
-                        if (has_b) o2[p.out_cols] = hi(v);
+                        if (has_b) o2[p.stream.copy_pitch] = hi(v);
                     }
                 }
             }
@@ -1016,6 +1020,50 @@ cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int6
         case 8: return launch_extract_r<8>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Delta columns over the frame axis, in place, one thread per (row, base column): rows[clip][f][cols * (1 + b) + c].
+//  kind 1: add_deltas, common/data_utils.py:50-58 -- d[f] = x[f] - x[f-1], d[0] = 0
+//  kind 2: inference/tflite/mfcc.h:432-441 -- d[f] = (x[min(f+1, n-1)] - x[max(f-1, 0)]) / 2
+//  kind 3: ... plus mfcc.h:443-453 -- the same difference of the delta column (recomputed from the base rows, which gives
+//          the stored values bit for bit)
+__global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ rows, const int32_t* __restrict__ lengths,
+                                                    int64_t n_items, int fpc, int cols, int pitch, int kind, int clip_len,
+                                                    int window, int hop, int pad_mode)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_items) return;
+    const int c = (int)(idx % cols);
+    const int64_t rf = idx / cols;
+    const int f = (int)(rf % fpc);
+    const int64_t clip = rf / fpc;
+    int n = fpc;                                        // rows this clip has
+    if (pad_mode == SCF_PAD_NONE && lengths != nullptr) {
+        const int len = min(max(lengths[clip], 0), clip_len);
+        n = len >= window ? (len - window) / hop + 1 : 0;
+    }
+    if (f >= n) return;
+    float* base = rows + clip * (int64_t)fpc * pitch + c;
+    auto X = [&](int j) { return base[(int64_t)j * pitch]; };
+    if (kind == SCF_DELTA_DIFF) {
+        base[(int64_t)f * pitch + cols] = f == 0 ? 0.f : X(f) - X(f - 1);
+        return;
+    }
+    auto D = [&](int j) { return (X(min(j + 1, n - 1)) - X(max(j - 1, 0))) / 2; };
+    base[(int64_t)f * pitch + cols] = D(f);
+    if (kind == SCF_DELTA_CENTRAL2) base[(int64_t)f * pitch + 2 * cols] = (D(min(f + 1, n - 1)) - D(max(f - 1, 0))) / 2;
+}
+
+cudaError_t launch_delta(float* rows, const int32_t* lengths, int64_t n_clips, int frames_per_clip, int cols, int pitch,
+                         int kind, int clip_len, int window, int hop, int pad_mode, cudaStream_t st)
+{
+    const int64_t n_items = n_clips * frames_per_clip * cols;
+    if (n_items <= 0) return cudaSuccess;
+    delta_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(rows, lengths, n_items, frames_per_clip, cols, pitch, kind,
+                                                                  clip_len, window, hop, pad_mode);
+    count_launch(1);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

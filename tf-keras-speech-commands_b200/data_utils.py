@@ -15,10 +15,11 @@ from .params import pr
 from .plan import BANK_MEL_SONOPY, OUT_CEPSTRUM, PAD_FRONT_ZERO, PAD_NONE, get_plan
 
 
-def _mfcc_plan():
+def _mfcc_plan(delta=None):
+    """The plan for the CURRENT ``pr``; delta='diff' appends the Python path's delta columns on the device."""
     return get_plan(sample_rate=int(pr.sample_rate), window=int(pr.window_samples), hop=int(pr.hop_samples),
                     n_fft=int(pr.n_fft), n_filt=int(pr.n_filt), n_coeffs=int(pr.n_mfcc), bank=BANK_MEL_SONOPY,
-                    output=OUT_CEPSTRUM)
+                    output=OUT_CEPSTRUM, delta=delta)
 
 
 def buffer_to_audio(buffer):
@@ -34,7 +35,8 @@ def audio_to_buffer(audio):
 
 
 def add_deltas(features, kind='diff'):
-    """appends delta features on the last axis.
+    """appends delta features on the last axis (host helper for arrays that are already on the host, as in the
+    reference; the feature entry points below compute their delta columns on the GPU, scf_config.delta).
     kind='diff'    : the Python path (common/data_utils.py:50-58): first difference, row 0 -> zeros;
     kind='central' : the C++ twin (inference/tflite/mfcc.h:432-441): (f[i+1] - f[i-1]) / 2 with the edges clamped."""
     features = np.asarray(features)
@@ -70,14 +72,11 @@ def audio_to_feature(audio_data):
     a = np.asarray(audio_data)[:pr.max_samples]
     if a.dtype != np.int16:
         a = a.astype(np.float32, copy=False)
-    if len(a) == 0:
-        raise ValueError('Cannot vectorize empty audio!')
+    # (empty audio is front-padded to max_samples like any short clip, common/data_utils.py:79-80: all-silence rows)
     buf = np.zeros((1, pr.max_samples), dtype=a.dtype)
     buf[0, :len(a)] = a                                    # the kernel applies the front padding itself
-    feature = _mfcc_plan().extract_host(buf, lengths=[len(a)], pad=PAD_FRONT_ZERO)[0]
-    if pr.use_delta:
-        feature = add_deltas(feature)
-    return feature
+    # pr.use_delta: the delta columns (common/data_utils.py:50-58, :85) come out of the same call
+    return _mfcc_plan('diff' if pr.use_delta else None).extract_host(buf, lengths=[len(a)], pad=PAD_FRONT_ZERO)[0]
 
 
 def load_wav(audio_path):
@@ -118,7 +117,6 @@ def extract_features_batch(clips, lengths=None):
         buf[:, :min(L, m)] = a[:, :m]
         a = buf
     full = bool((lengths == m).all())
-    feats = _mfcc_plan().extract_host(a, lengths=None if full else lengths, pad=PAD_FRONT_ZERO)
-    if pr.use_delta:
-        feats = np.stack([add_deltas(f) for f in feats])
+    feats = _mfcc_plan('diff' if pr.use_delta else None).extract_host(a, lengths=None if full else lengths,
+                                                                      pad=PAD_FRONT_ZERO)
     return feats[..., None]

@@ -4,15 +4,16 @@
 State per stream lives on the GPU (carry < window samples + ring of n_features rows, double buffered); each push is
 ONE launch of the fused MFCC kernel, which reads concat(carry, chunk), writes the new ring rows and carries the state
 over (include/scfeat.h, scf_stream_*).
-use_delta is applied to the returned copy only (the reference re-applies it to the already widened
-ring every chunk, listen.py:111-112, which is a bug this does not copy).
+use_delta: the delta columns of the returned ring are computed on the device from the ring's base columns (the
+reference re-applies add_deltas to the already widened ring every chunk, listen.py:111-112, which is a bug this does
+not copy).  Every call returns a fresh array, as the reference does.
 """
 import ctypes
 
 import numpy as np
 
 from . import _lib
-from .data_utils import _mfcc_plan, add_deltas
+from .data_utils import _mfcc_plan
 from .params import pr
 
 
@@ -20,11 +21,11 @@ class FeatureStream:
     """n_streams concurrent listeners sharing one configuration (the current ``pr``)."""
 
     def __init__(self, n_streams=1, max_chunk=4096):
-        self.plan = _mfcc_plan()
+        self.use_delta = bool(pr.use_delta)
+        self.plan = _mfcc_plan('diff' if self.use_delta else None)      # delta columns of the returned ring: on the device
         self.n_streams = int(n_streams)
         self.rows = int(pr.n_features)
         self.cols = self.plan.out_cols
-        self.use_delta = bool(pr.use_delta)
         self.max_chunk = int(max_chunk)
         self._h = ctypes.c_void_p()
         _lib.check(_lib.lib().scf_stream_create(self.plan.handle, self.n_streams, self.rows, self.max_chunk,
@@ -47,14 +48,17 @@ class FeatureStream:
     def reset(self):
         _lib.check(_lib.lib().scf_stream_reset(self._h, None))
 
-    def push(self, chunks):
+    def push(self, chunks, copy=True):
         """chunks: int16 [n_streams, chunk_len].  Returns (ring [n_streams, rows, cols] float32 oldest->newest,
-        new_rows [n_streams] int32)."""
+        new_rows [n_streams] int32) -- fresh arrays, like the reference, unless copy=False (then views of buffers the
+        next push overwrites)."""
         c = np.ascontiguousarray(chunks, dtype=np.int16)
         if c.ndim != 2 or c.shape[0] != self.n_streams:
             raise ValueError('chunks must be [n_streams, chunk_len]')
         _lib.check(_lib.lib().scf_stream_push_host_i16(self._h, c.ctypes.data, c.shape[1], self._ring.ctypes.data,
                                                        self._new.ctypes.data))
+        if copy:
+            return self._ring.copy(), self._new.copy()
         return self._ring, self._new
 
     def push_device(self, d_chunks, chunk_len, d_ring_out=None, d_new_rows=None, stream=0):
@@ -72,10 +76,7 @@ class Listener:
         """chunk: raw 16-bit LE mono bytes -> (n_features, feature_size, 1) float32"""
         pcm = np.frombuffer(chunk, dtype='<i2')
         if len(pcm) == 0:
-            ring = self._fs._ring
+            ring = self._fs._ring.copy()
         else:
             ring, _ = self._fs.push(pcm[None, :])
-        feats = ring[0]
-        if self._fs.use_delta:
-            feats = add_deltas(feats)
-        return np.expand_dims(feats, axis=-1)
+        return np.expand_dims(ring[0], axis=-1)
