@@ -159,10 +159,21 @@ int scf_host_sync(const scf_plan* plan);
 
 /* Library-owned output handed over as a DLPack capsule payload: *dl_out is a DLManagedTensor*
  * (kDLCUDA, float32, shape [n_clips, frames_per_clip, out_cols]) whose deleter frees the device
- * buffer; consumable by tf.experimental.dlpack.from_dlpack / torch.from_dlpack. */
+ * buffer; consumable by tf.experimental.dlpack.from_dlpack / torch.from_dlpack.  The buffer comes from the stream-
+ * ordered allocator (cudaMallocAsync on cuda_stream), so the call only enqueues work. */
 int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips, int64_t clip_stride,
                            int32_t clip_len, const int32_t* d_lengths, int32_t pad, void** dl_out,
                            void* cuda_stream);
+
+/* Device-resident feature sets for the framework (classifier/data.py:97-120 loads every feature into memory for
+ * model.fit): float32 kDLCUDA tensors of 1..4 dimensions, e.g. [N, n_features, feature_size, 1].
+ * scf_dlpack_alloc : a library-owned buffer (freed by the DLPack deleter); *d_ptr_out (nullable) is its device pointer,
+ *                    to be filled by scf_extract_* / scf_ingest_wavs_device before the tensor is handed over.
+ * scf_dlpack_wrap  : a descriptor over memory the CALLER owns (e.g. the gathered multi-GPU cache); the deleter calls
+ *                    release(release_ctx) once instead of freeing. */
+int scf_dlpack_alloc(int32_t device, const int64_t* shape, int32_t ndim, void** dl_out, void** d_ptr_out);
+int scf_dlpack_wrap(void* d_ptr, int32_t device, const int64_t* shape, int32_t ndim, void (*release)(void*),
+                    void* release_ctx, void** dl_out);
 
 /* Python-only helper: wraps a DLManagedTensor* from scf_extract_i16_dlpack in a PyCapsule named "dltensor"
  * whose destructor calls the tensor's deleter unless a consumer took ownership (renamed it "used_dltensor").
@@ -190,6 +201,28 @@ int scf_stream_push_i16(scf_stream* s, const int16_t* d_chunks, int32_t chunk_le
                         int32_t* d_new_rows, void* cuda_stream);
 int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chunk_len, float* h_ring_out,
                              int32_t* h_new_rows);
+
+/* ---- PCM ingest: replaces the per-file loop classifier/data.py:30-46 -> get_mfcc_feature (common/data_utils.py:89-97:
+ *      librosa.load(path, sr, mono=True) + audio_to_feature's head crop :77) for files already at the plan's rate ---- */
+
+/* RIFF/WAVE header parse + PCM read of n_files 16-bit PCM wav files with n_threads reader threads (host only, no GPU).
+ * File i goes to h_pcm[i*clip_stride ..): its FIRST min(frames, clip_len) samples (multi-channel files are mixed down to
+ * mono), zeros behind them; h_lengths[i] = the number of valid samples.  Fails (message names the file) on a file that
+ * is unreadable, not 16-bit PCM, or whose rate differs from sample_rate (no resampler). */
+int scf_wav_read_batch(const char* const* paths, int64_t n_files, int32_t sample_rate, int32_t clip_len, int16_t* h_pcm,
+                       int64_t clip_stride, int32_t* h_lengths, int32_t n_threads);
+
+/* wav files -> feature rows, pipelined: reader threads fill pinned staging slots of `batch` clips while earlier slots are
+ * uploaded, transformed and downloaded by scf_extract_host_i16_async's two device slots; short clips are padded with
+ * zeros in FRONT by the kernel (SCF_PAD_FRONT_ZERO).  h_out: [n_files][frames(clip_len)][out_cols] (pinned or pageable);
+ * h_lengths_out (nullable): the valid samples of every file.  Synchronous: everything is complete on return. */
+int scf_ingest_wavs(const scf_plan* plan, const char* const* paths, int64_t n_files, int32_t clip_len, int32_t batch,
+                    int32_t n_threads, float* h_out, int32_t* h_lengths_out);
+
+/* Same pipeline with the features left on the device: d_out [n_files][frames(clip_len)][out_cols] on the plan's device
+ * (e.g. the buffer of scf_dlpack_alloc).  Synchronous. */
+int scf_ingest_wavs_device(const scf_plan* plan, const char* const* paths, int64_t n_files, int32_t clip_len, int32_t batch,
+                           int32_t n_threads, float* d_out, int32_t* h_lengths_out);
 
 /* ---- streaming post-processing on the device: replaces the per-chunk scalar work listen.py does after the model,
  *      ThresholdDecoder (listen.py:452-521; C++ twin inference/tflite/threshold_decoder.h:19-113) and

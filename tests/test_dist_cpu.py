@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import sonopy as osonopy
-from scfeat.dist import gathered_row_of, shard_range
+from scfeat.dist import shard_range
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -30,10 +30,7 @@ def test_shard_range_partitions_the_clips(n, world):
         seen += list(range(start, start + count))
         if count:
             assert start == r * per_rank
-    assert seen == list(range(n))
-    for c in (0, n // 2, n - 1):
-        if n:
-            assert gathered_row_of(c, n, world) == c
+    assert seen == list(range(n))             # rank-major blocks of per_rank rows: the gathered cache is in clip order
     if n == 105829 and world == 8:
         assert per == 13229
 

@@ -61,8 +61,16 @@ def test_feature_cache_gather_single_process(example_pcm):
     d = torch.from_numpy(pcm).cuda()
     g.extract_and_gather(d.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert np.array_equal(g.to_host(), plan.extract_host(pcm))
-    g.close()
+    want = plan.extract_host(pcm)
+    assert np.array_equal(g.to_host(), want)
+    # the gathered cache handed to the framework through DLPack: [N, 30, 20, 1] on the device, kept alive by the tensor
+    t = torch.from_dlpack(g.to_dlpack())
+    assert t.is_cuda and tuple(t.shape) == (len(pcm), 30, 20, 1) and t.data_ptr() == g.ptr
+    del g
+    import gc
+    gc.collect()
+    assert np.array_equal(t.cpu().numpy()[..., 0], want)          # still valid: the capsule owns a reference to the cache
+    del t
 
 
 def test_two_gpus_over_ipc_when_available():

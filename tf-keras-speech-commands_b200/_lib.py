@@ -37,6 +37,7 @@ EXPORTS = [
     'scf_ipc_import', 'scf_ipc_close',
     'scf_post_build_cd', 'scf_post_create', 'scf_post_destroy', 'scf_post_reset', 'scf_post_decode', 'scf_post_step',
     'scf_post_trigger_update', 'scf_post_state', 'scf_post_info',
+    'scf_wav_read_batch', 'scf_ingest_wavs', 'scf_ingest_wavs_device', 'scf_dlpack_alloc', 'scf_dlpack_wrap',
 ]
 
 
@@ -137,6 +138,11 @@ def lib():
         L.scf_post_trigger_update.argtypes = [vp, vp, vp, vp, vp]
         L.scf_post_state.argtypes = [vp, vp, vp, vp]
         L.scf_post_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
+        L.scf_wav_read_batch.argtypes = [vp, i64, i32, i32, vp, i64, vp, i32]
+        L.scf_ingest_wavs.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+        L.scf_ingest_wavs_device.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+        L.scf_dlpack_alloc.argtypes = [i32, vp, i32, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+        L.scf_dlpack_wrap.argtypes = [vp, i32, vp, i32, vp, vp, ctypes.POINTER(vp)]
         _lib = L
         return _lib
 
@@ -189,6 +195,13 @@ def bank_apply_tasks(power_a, power_b, **kw):
     check(lib().scf_bank_apply_tasks(ctypes.byref(c), pa.ctypes.data, pb.ctypes.data, sa.ctypes.data, sb.ctypes.data,
                                      st.ctypes.data))
     return sa, sb, dict(zip(('tasks', 'partial_rows', 'groups', 'longest_group'), (int(v) for v in st)))
+
+
+def path_array(paths):
+    """list of str -> (char*[] for the C ABI, keep-alive object)"""
+    enc = [os.fsencode(p) for p in paths]
+    arr = (ctypes.c_char_p * len(enc))(*enc)
+    return arr, enc
 
 
 def num_frames(n_samples, window, hop):

@@ -764,7 +764,8 @@ static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int
 }
 
 static int extract_host_async(const scf_plan* plan, const int16_t* h_in, int64_t n_clips, int64_t clip_stride,
-                              int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out)
+                              int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out,
+                              cudaStream_t* used = nullptr)
 {
     if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
     if (n_clips < 0 || clip_len < 0) return fail(SCF_ERR_INVALID, "negative size");
@@ -779,6 +780,7 @@ static int extract_host_async(const scf_plan* plan, const int16_t* h_in, int64_t
     std::lock_guard<std::mutex> lock(ws.mu);
     Workspace::Slot& sl = ws.slot[ws.next_slot++ & 1];
     if (!sl.st) SCF_CUDA(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+    if (used) *used = sl.st;
     const size_t in_bytes = (size_t)((n_clips - 1) * clip_stride + clip_len) * 2;
     const size_t out_bytes = (size_t)n_clips * fpc * plan->out_cols * sizeof(float);
     if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes || (h_lengths && (size_t)n_clips * 4 > sl.len_bytes))
@@ -800,6 +802,19 @@ static int extract_host_async(const scf_plan* plan, const int16_t* h_in, int64_t
     return SCF_OK;
 }
 
+// for scfeat_ingest.cu
+int extract_host_async_on(const scf_plan* plan, const int16_t* h_in, int64_t n_clips, int64_t clip_stride, int32_t clip_len,
+                          const int32_t* h_lengths, int32_t pad, float* h_out, cudaStream_t* used)
+{
+    return extract_host_async(plan, h_in, n_clips, clip_stride, clip_len, h_lengths, pad, h_out, used);
+}
+int plan_sample_rate(const scf_plan* plan) { return plan->cfg.sample_rate; }
+int plan_device(const scf_plan* plan) { return plan->device; }
+int64_t plan_row_floats(const scf_plan* plan, int32_t clip_len)
+{
+    return scf_num_frames(clip_len, plan->cfg.window, plan->cfg.hop) * (int64_t)plan->out_cols;
+}
+
 static int host_sync(const scf_plan* plan)
 {
     if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
@@ -816,20 +831,66 @@ static int host_sync(const scf_plan* plan)
 // ---------------------------------------------------------------------------------------------
 struct DlOwner {
     DLManagedTensor mt;
-    int64_t shape[3];
+    int64_t shape[4];
     int device;
+    void (*release)(void*) = nullptr;      // wrapped buffers: tells the owner instead of freeing
+    void* release_ctx = nullptr;
 };
 
 static void dl_deleter(DLManagedTensor* self)
 {
     if (!self) return;
     DlOwner* o = static_cast<DlOwner*>(self->manager_ctx);
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(o->device);
-    cudaFree(self->dl_tensor.data);
-    if (prev >= 0) cudaSetDevice(prev);
+    if (o->release) {
+        o->release(o->release_ctx);
+    } else {
+        // cudaFree synchronises the device: a consumer may still have work in flight on streams this library does not
+        // know about when it drops the tensor, so the release is the one place where that is wanted
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(o->device);
+        cudaFree(self->dl_tensor.data);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
     delete o;
+}
+
+// float32 kDLCUDA tensor descriptor over `data`
+static DlOwner* dl_make(void* data, int device, const int64_t* shape, int ndim)
+{
+    DlOwner* o = new (std::nothrow) DlOwner();
+    if (!o) return nullptr;
+    o->device = device;
+    for (int i = 0; i < ndim; ++i) o->shape[i] = shape[i];
+    o->mt.dl_tensor.data = data;
+    o->mt.dl_tensor.device.device_type = kDLCUDA;
+    o->mt.dl_tensor.device.device_id = device;
+    o->mt.dl_tensor.ndim = ndim;
+    o->mt.dl_tensor.dtype.code = kDLFloat;
+    o->mt.dl_tensor.dtype.bits = 32;
+    o->mt.dl_tensor.dtype.lanes = 1;
+    o->mt.dl_tensor.shape = o->shape;
+    o->mt.dl_tensor.strides = nullptr;
+    o->mt.dl_tensor.byte_offset = 0;
+    o->mt.manager_ctx = o;
+    o->mt.deleter = dl_deleter;
+    return o;
+}
+
+// Stream-ordered allocation for library-owned outputs: cudaMallocAsync does not synchronise the device (cudaMalloc does),
+// so scf_extract_i16_dlpack stays an enqueue-only call.  The pool keeps its memory between calls.
+static cudaError_t alloc_on_stream(void** ptr, size_t bytes, int device, cudaStream_t st)
+{
+    static std::once_flag once[16];
+    std::call_once(once[device & 15], [device] {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    });
+    return cudaMallocAsync(ptr, bytes, st);
 }
 
 }  // namespace scf
@@ -995,30 +1056,54 @@ int scf_extract_i16_dlpack(const scf_plan* plan, const int16_t* d_pcm, int64_t n
     const int64_t fpc = scf_num_frames(clip_len, plan->cfg.window, plan->cfg.hop);
     DeviceGuard guard(plan->device);
     if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
-    DlOwner* o = new (std::nothrow) DlOwner();
-    if (!o) return fail(SCF_ERR_ALLOC, "out of host memory");
     const size_t bytes = std::max<size_t>((size_t)n_clips * fpc * plan->out_cols * sizeof(float), 256);
     float* d_out = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_out, bytes);
-    if (e != cudaSuccess) { delete o; return fail(SCF_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    cudaError_t e = alloc_on_stream((void**)&d_out, bytes, plan->device, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return fail(SCF_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
     if (pad == SCF_PAD_NONE && d_lengths) cudaMemsetAsync(d_out, 0, bytes, (cudaStream_t)cuda_stream);
     int rc = extract_device(plan, false, d_pcm, n_clips, clip_stride, clip_len, d_lengths, pad, d_out, nullptr, 0, 0,
                             cuda_stream);
-    if (rc) { cudaFree(d_out); delete o; return rc; }
-    o->device = plan->device;
-    o->shape[0] = n_clips; o->shape[1] = fpc; o->shape[2] = plan->out_cols;
-    o->mt.dl_tensor.data = d_out;
-    o->mt.dl_tensor.device.device_type = kDLCUDA;
-    o->mt.dl_tensor.device.device_id = plan->device;
-    o->mt.dl_tensor.ndim = 3;
-    o->mt.dl_tensor.dtype.code = kDLFloat;
-    o->mt.dl_tensor.dtype.bits = 32;
-    o->mt.dl_tensor.dtype.lanes = 1;
-    o->mt.dl_tensor.shape = o->shape;
-    o->mt.dl_tensor.strides = nullptr;
-    o->mt.dl_tensor.byte_offset = 0;
-    o->mt.manager_ctx = o;
-    o->mt.deleter = dl_deleter;
+    const int64_t shape[3] = {n_clips, fpc, plan->out_cols};
+    DlOwner* o = rc ? nullptr : dl_make(d_out, plan->device, shape, 3);
+    if (!o) {
+        cudaFreeAsync(d_out, (cudaStream_t)cuda_stream);
+        return rc ? rc : fail(SCF_ERR_ALLOC, "out of host memory");
+    }
+    *dl_out = &o->mt;
+    return SCF_OK;
+}
+
+int scf_dlpack_alloc(int32_t device, const int64_t* shape, int32_t ndim, void** dl_out, void** d_ptr_out)
+{
+    if (!shape || !dl_out || ndim < 1 || ndim > 4) return fail(SCF_ERR_INVALID, "bad argument");
+    *dl_out = nullptr;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(SCF_ERR_CUDA, "cudaSetDevice failed");
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] < 0) return fail(SCF_ERR_INVALID, "negative extent");
+        n *= (size_t)shape[i];
+    }
+    void* d = nullptr;
+    SCF_CUDA(cudaMalloc(&d, std::max<size_t>(n * sizeof(float), 256)));
+    DlOwner* o = dl_make(d, device, shape, ndim);
+    if (!o) { cudaFree(d); return fail(SCF_ERR_ALLOC, "out of host memory"); }
+    *dl_out = &o->mt;
+    if (d_ptr_out) *d_ptr_out = d;
+    return SCF_OK;
+}
+
+int scf_dlpack_wrap(void* d_ptr, int32_t device, const int64_t* shape, int32_t ndim, void (*release)(void*),
+                    void* release_ctx, void** dl_out)
+{
+    if (!d_ptr || !shape || !dl_out || !release || ndim < 1 || ndim > 4) return fail(SCF_ERR_INVALID, "bad argument");
+    *dl_out = nullptr;
+    if (device < 0) SCF_CUDA(cudaGetDevice(&device));
+    DlOwner* o = dl_make(d_ptr, device, shape, ndim);
+    if (!o) return fail(SCF_ERR_ALLOC, "out of host memory");
+    o->release = release;
+    o->release_ctx = release_ctx;
     *dl_out = &o->mt;
     return SCF_OK;
 }

@@ -1,0 +1,293 @@
+// PCM ingest for the feature path: what sits in front of the kernels when a feature cache is
+// built from a tree of wav files -- the per-file loop classifier/data.py:30-46 -> get_mfcc_feature
+// (common/data_utils.py:89-97) -> librosa.load(path, sr, mono=True) + audio_to_feature's head crop (:77).
+//
+//   scf_wav_read_batch : RIFF/WAVE header parse + PCM read of a batch of files, a few reader threads, straight into a
+//                        caller buffer [n][clip_stride] int16 with per-clip lengths (the front padding of short clips
+//                        happens in the loader of the extraction kernel, so nothing is shifted on the host)
+//   scf_ingest_wavs    : the whole pipeline -- reader threads fill pinned staging slots while earlier slots are
+//                        uploaded, transformed and downloaded by scf_extract_host_i16_async's two device slots
+//
+// Resampling is out of scope (the reference leaves it to librosa): a file whose rate differs from the plan's is an error.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "scfeat_internal.h"
+
+namespace scf {
+
+int post_fail(int code, const char* msg);   // scfeat_host.cu: sets scf_last_error
+int extract_host_async_on(const scf_plan* plan, const int16_t* h_in, int64_t n_clips, int64_t clip_stride, int32_t clip_len,
+                          const int32_t* h_lengths, int32_t pad, float* h_out, cudaStream_t* used);   // scfeat_host.cu
+int plan_sample_rate(const scf_plan* plan);
+int plan_device(const scf_plan* plan);
+int64_t plan_row_floats(const scf_plan* plan, int32_t clip_len);
+
+struct WavInfo {
+    int channels = 0, rate = 0, bits = 0, format = 0;
+    long data_off = 0;
+    long long data_bytes = 0;
+};
+
+static inline uint32_t le32(const unsigned char* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint32_t le16(const unsigned char* p) { return p[0] | (p[1] << 8); }
+
+// Walks the RIFF chunks up to "data" (what Python's `wave` module does for the reference's files).
+static bool parse_wav(FILE* f, WavInfo& w, std::string& why)
+{
+    unsigned char h[12];
+    if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) != 0 || memcmp(h + 8, "WAVE", 4) != 0) {
+        why = "not a RIFF/WAVE file";
+        return false;
+    }
+    bool have_fmt = false;
+    for (;;) {
+        unsigned char c[8];
+        if (fread(c, 1, 8, f) != 8) { why = "no data chunk"; return false; }
+        const uint32_t size = le32(c + 4);
+        if (memcmp(c, "fmt ", 4) == 0) {
+            unsigned char b[40];
+            const size_t n = std::min<size_t>(size, sizeof(b));
+            if (size < 16 || fread(b, 1, n, f) != n) { why = "short fmt chunk"; return false; }
+            w.format = (int)le16(b);
+            w.channels = (int)le16(b + 2);
+            w.rate = (int)le32(b + 4);
+            w.bits = (int)le16(b + 14);
+            if (w.format == 0xFFFE && n >= 26) w.format = (int)le16(b + 24);      // WAVE_FORMAT_EXTENSIBLE: sub-format
+            have_fmt = true;
+            const long skip = (long)(size - n) + (long)(size & 1);
+            if (skip && fseek(f, skip, SEEK_CUR) != 0) { why = "truncated file"; return false; }
+        } else if (memcmp(c, "data", 4) == 0) {
+            if (!have_fmt) { why = "data chunk before fmt chunk"; return false; }
+            w.data_off = ftell(f);
+            w.data_bytes = size;
+            return true;
+        } else {
+            if (fseek(f, (long)size + (long)(size & 1), SEEK_CUR) != 0) { why = "truncated file"; return false; }
+        }
+    }
+}
+
+// One file -> row `dst` (clip_len samples, zero filled behind the data); returns the number of valid samples or -1.
+static int read_one(const char* path, int sample_rate, int clip_len, int16_t* dst, std::vector<int16_t>& scratch, std::string& why)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) { why = "cannot open"; return -1; }
+    WavInfo w;
+    if (!parse_wav(f, w, why)) { fclose(f); return -1; }
+    if (w.format != 1 || w.bits != 16) { fclose(f); why = "only 16-bit PCM wav is supported"; return -1; }
+    if (w.channels < 1) { fclose(f); why = "no channels"; return -1; }
+    if (w.rate != sample_rate) {
+        fclose(f);
+        why = "sample rate " + std::to_string(w.rate) + " != " + std::to_string(sample_rate) + " (no resampler)";
+        return -1;
+    }
+    const long long frames_in_file = w.data_bytes / (2LL * w.channels);
+    const int want = (int)std::min<long long>(frames_in_file, clip_len);        // keep the FIRST clip_len samples
+    int got;
+    if (w.channels == 1) {
+        got = (int)fread(dst, 2, (size_t)want, f);
+    } else {
+        scratch.resize((size_t)want * w.channels);
+        got = (int)(fread(scratch.data(), 2, scratch.size(), f) / w.channels);
+        for (int i = 0; i < got; ++i) {                                         // mono mix-down: float32 mean, round half to even
+            float acc = 0.f;
+            for (int c = 0; c < w.channels; ++c) acc += (float)scratch[(size_t)i * w.channels + c];
+            dst[i] = (int16_t)nearbyintf(acc / (float)w.channels);
+        }
+    }
+    fclose(f);
+    if (got < clip_len) memset(dst + got, 0, (size_t)(clip_len - got) * 2);
+    return got;
+}
+
+// files [0, n) of `paths` into rows of h_pcm; returns the index of the first file that failed or -1
+static int64_t read_range(const char* const* paths, int64_t n, int sample_rate, int clip_len, int16_t* h_pcm,
+                          int64_t clip_stride, int32_t* h_lengths, int n_threads, std::string& why)
+{
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n));
+    std::atomic<int64_t> next{0}, bad{-1};
+    std::string bad_why;                                                        // written by the one thread that sets `bad`
+    auto work = [&]() {
+        std::vector<int16_t> scratch;
+        std::string w;
+        for (;;) {
+            const int64_t i0 = next.fetch_add(16);                              // small blocks of neighbouring files
+            if (i0 >= n) break;
+            for (int64_t i = i0; i < std::min<int64_t>(n, i0 + 16); ++i) {
+                const int got = read_one(paths[i], sample_rate, clip_len, h_pcm + i * clip_stride, scratch, w);
+                h_lengths[i] = got < 0 ? 0 : got;
+                if (got < 0) {
+                    int64_t expect = -1;
+                    if (bad.compare_exchange_strong(expect, i)) bad_why = std::string(paths[i]) + ": " + w;
+                }
+            }
+        }
+    };
+    if (n_threads == 1) {
+        work();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+        for (auto& x : th) x.join();
+    }
+    if (bad.load() >= 0) why = bad_why;
+    return bad.load();
+}
+
+}  // namespace scf
+
+using namespace scf;
+
+extern "C" {
+
+int scf_wav_read_batch(const char* const* paths, int64_t n_files, int32_t sample_rate, int32_t clip_len, int16_t* h_pcm,
+                       int64_t clip_stride, int32_t* h_lengths, int32_t n_threads)
+{
+    if (n_files < 0 || clip_len < 1 || clip_stride < clip_len) return post_fail(SCF_ERR_INVALID, "bad size");
+    if (n_files == 0) return SCF_OK;
+    if (!paths || !h_pcm || !h_lengths) return post_fail(SCF_ERR_INVALID, "NULL argument");
+    std::string why;
+    if (read_range(paths, n_files, sample_rate, clip_len, h_pcm, clip_stride, h_lengths, n_threads, why) >= 0)
+        return post_fail(SCF_ERR_INVALID, why.c_str());
+    return SCF_OK;
+}
+
+int scf_ingest_wavs(const scf_plan* plan, const char* const* paths, int64_t n_files, int32_t clip_len, int32_t batch,
+                    int32_t n_threads, float* h_out, int32_t* h_lengths_out)
+{
+    if (!plan) return post_fail(SCF_ERR_INVALID, "plan is NULL");
+    if (n_files < 0 || clip_len < 1 || batch < 1) return post_fail(SCF_ERR_INVALID, "bad size");
+    if (n_files == 0) return SCF_OK;
+    if (!paths || !h_out) return post_fail(SCF_ERR_INVALID, "NULL argument");
+    const int rate = plan_sample_rate(plan);
+    const int64_t row_floats = plan_row_floats(plan, clip_len);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(plan_device(plan));
+    // pinned staging ring: a slot is refilled only after the upload that read it has finished
+    constexpr int kSlots = 3;
+    int16_t* pcm[kSlots] = {nullptr, nullptr, nullptr};
+    int32_t* len[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};
+    bool used[kSlots] = {false, false, false};
+    int rc = SCF_OK;
+    std::string why;
+    const int64_t nb = std::min<int64_t>(batch, n_files);
+    for (int s = 0; s < kSlots && rc == SCF_OK; ++s) {
+        if (cudaHostAlloc((void**)&pcm[s], (size_t)nb * clip_len * 2, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&len[s], (size_t)nb * 4, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            rc = post_fail(SCF_ERR_ALLOC, "pinned staging allocation failed");
+        }
+    }
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_files && rc == SCF_OK; f0 += nb, slot = (slot + 1) % kSlots) {
+        const int64_t n = std::min<int64_t>(nb, n_files - f0);
+        if (used[slot] && cudaEventSynchronize(done[slot]) != cudaSuccess) { rc = post_fail(SCF_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+        if (read_range(paths + f0, n, rate, clip_len, pcm[slot], clip_len, len[slot], n_threads, why) >= 0) {
+            rc = post_fail(SCF_ERR_INVALID, why.c_str());
+            break;
+        }
+        if (h_lengths_out) memcpy(h_lengths_out + f0, len[slot], (size_t)n * 4);
+        cudaStream_t st = nullptr;
+        rc = extract_host_async_on(plan, pcm[slot], n, clip_len, clip_len, len[slot], SCF_PAD_FRONT_ZERO,
+                                   h_out + f0 * row_floats, &st);
+        if (rc) break;
+        // (the event sits behind the slot's upload, kernel and download: simple, and the reader is two slots ahead)
+        if (st != nullptr) {
+            if (cudaEventRecord(done[slot], st) != cudaSuccess) { rc = post_fail(SCF_ERR_CUDA, "cudaEventRecord failed"); break; }
+            used[slot] = true;
+        }
+    }
+    const int rc_sync = scf_host_sync(plan);
+    if (rc == SCF_OK) rc = rc_sync;
+    for (int s = 0; s < kSlots; ++s) {
+        if (pcm[s]) cudaFreeHost(pcm[s]);
+        if (len[s]) cudaFreeHost(len[s]);
+        if (done[s]) cudaEventDestroy(done[s]);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+// Same pipeline with the features left on the device (the training set handed to the framework through DLPack never
+// visits the host): pinned staging slots -> per-slot device PCM buffers -> scf_extract_i16 into d_out.
+int scf_ingest_wavs_device(const scf_plan* plan, const char* const* paths, int64_t n_files, int32_t clip_len, int32_t batch,
+                           int32_t n_threads, float* d_out, int32_t* h_lengths_out)
+{
+    if (!plan) return post_fail(SCF_ERR_INVALID, "plan is NULL");
+    if (n_files < 0 || clip_len < 1 || batch < 1) return post_fail(SCF_ERR_INVALID, "bad size");
+    if (n_files == 0) return SCF_OK;
+    if (!paths || !d_out) return post_fail(SCF_ERR_INVALID, "NULL argument");
+    const int rate = plan_sample_rate(plan);
+    const int64_t row_floats = plan_row_floats(plan, clip_len);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(plan_device(plan));
+    constexpr int kSlots = 3;
+    int16_t* pcm[kSlots] = {nullptr, nullptr, nullptr};
+    int32_t* len[kSlots] = {nullptr, nullptr, nullptr};
+    int16_t* d_pcm[kSlots] = {nullptr, nullptr, nullptr};
+    int32_t* d_len[kSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};
+    bool used[kSlots] = {false, false, false};
+    cudaStream_t st = nullptr;
+    int rc = SCF_OK;
+    std::string why;
+    const int64_t nb = std::min<int64_t>(batch, n_files);
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = post_fail(SCF_ERR_CUDA, "cudaStreamCreate failed");
+    for (int s = 0; s < kSlots && rc == SCF_OK; ++s) {
+        if (cudaHostAlloc((void**)&pcm[s], (size_t)nb * clip_len * 2, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void**)&len[s], (size_t)nb * 4, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc((void**)&d_pcm[s], (size_t)nb * clip_len * 2) != cudaSuccess ||
+            cudaMalloc((void**)&d_len[s], (size_t)nb * 4) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            rc = post_fail(SCF_ERR_ALLOC, "staging allocation failed");
+        }
+    }
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_files && rc == SCF_OK; f0 += nb, slot = (slot + 1) % kSlots) {
+        const int64_t n = std::min<int64_t>(nb, n_files - f0);
+        if (used[slot] && cudaEventSynchronize(done[slot]) != cudaSuccess) { rc = post_fail(SCF_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+        if (read_range(paths + f0, n, rate, clip_len, pcm[slot], clip_len, len[slot], n_threads, why) >= 0) {
+            rc = post_fail(SCF_ERR_INVALID, why.c_str());
+            break;
+        }
+        if (h_lengths_out) memcpy(h_lengths_out + f0, len[slot], (size_t)n * 4);
+        if (cudaMemcpyAsync(d_pcm[slot], pcm[slot], (size_t)n * clip_len * 2, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_len[slot], len[slot], (size_t)n * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            rc = post_fail(SCF_ERR_CUDA, "cudaMemcpyAsync failed");
+            break;
+        }
+        rc = scf_extract_i16(plan, d_pcm[slot], n, clip_len, clip_len, d_len[slot], SCF_PAD_FRONT_ZERO, d_out + f0 * row_floats, st);
+        if (rc) break;
+        if (cudaEventRecord(done[slot], st) != cudaSuccess) { rc = post_fail(SCF_ERR_CUDA, "cudaEventRecord failed"); break; }
+        used[slot] = true;
+    }
+    if (st) {
+        if (cudaStreamSynchronize(st) != cudaSuccess && rc == SCF_OK) rc = post_fail(SCF_ERR_CUDA, "cudaStreamSynchronize failed");
+        cudaStreamDestroy(st);
+    }
+    for (int s = 0; s < kSlots; ++s) {
+        if (pcm[s]) cudaFreeHost(pcm[s]);
+        if (len[s]) cudaFreeHost(len[s]);
+        if (d_pcm[s]) cudaFree(d_pcm[s]);
+        if (d_len[s]) cudaFree(d_len[s]);
+        if (done[s]) cudaEventDestroy(done[s]);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+}  // extern "C"

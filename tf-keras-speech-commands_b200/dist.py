@@ -24,12 +24,6 @@ def shard_range(n_clips, world, rank):
     return start, count, per_rank
 
 
-def gathered_row_of(clip, n_clips, world):
-    """Row block of global clip `clip` inside the gathered cache (rank-major, per_rank rows per rank)."""
-    per_rank = -(-int(n_clips) // int(world))
-    return (clip // per_rank) * per_rank + clip % per_rank      # == clip: the cache is laid out in clip order
-
-
 class FeatureCacheGather:
     """Per-rank cache [world * per_rank, frames, cols] float32, peer-mapped on every rank.
 
@@ -88,6 +82,15 @@ class FeatureCacheGather:
         check(_lib.lib().scf_memcpy(self.device, out.ctypes.data, self._own, self.bytes, 1, None))
         return out[:self.n_clips]
 
+    def to_dlpack(self):
+        """The gathered cache as a DLPack capsule [n_clips, frames, cols, 1] float32 on this rank's GPU -- what
+        classifier/data.py:97-120 assembles from 105k .npy files, handed to the framework without leaving the device
+        (tf.experimental.dlpack.from_dlpack / torch.from_dlpack).  Rank r's rows start at r * per_rank and the padding
+        rows of the last rank come last, so the first n_clips rows are the clips in order.  The cache stays alive
+        until the consumer releases the tensor; call after the closing barrier."""
+        from .plan import dlpack_wrap
+        return dlpack_wrap(self, self._own.value, (self.n_clips, self.frames, self.cols, 1), self.device)
+
     def close(self):
         for p in self._imported:
             _lib.lib().scf_ipc_close(self.device, p)
@@ -101,8 +104,3 @@ class FeatureCacheGather:
             self.close()
         except Exception:
             pass
-
-
-def gather_padding_note():
-    return ('rank r owns clips [r*ceil(N/R), min(N, (r+1)*ceil(N/R))); caches hold R*ceil(N/R) rows, the tail rows '
-            'of the last rank are padding and are trimmed by to_host()')

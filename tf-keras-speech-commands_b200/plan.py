@@ -126,6 +126,48 @@ def _make_capsule(ptr):
     return _pydll.scf_dlpack_make_capsule(ptr)
 
 
+def dlpack_alloc(shape, device=-1):
+    """Library-owned float32 device buffer of `shape` (1..4 dims): returns (device pointer, finish) where finish() turns
+    it into the PyCapsule "dltensor" whose deleter frees it.  Fill the buffer through the device entry points first."""
+    shp = (ctypes.c_int64 * len(shape))(*[int(v) for v in shape])
+    dl, ptr = ctypes.c_void_p(), ctypes.c_void_p()
+    check(_lib.lib().scf_dlpack_alloc(int(device), shp, len(shape), ctypes.byref(dl), ctypes.byref(ptr)))
+    return ptr.value, (lambda: _make_capsule(dl.value))
+
+
+_RELEASE_T = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+_wrapped = {}                      # token -> (owner object, callback): keeps both alive until the consumer lets go
+_wrapped_lock = threading.Lock()
+_wrapped_next = [1]
+_released = []                     # entries whose consumer let go: dropped at the next call, never inside their own callback
+
+
+def dlpack_wrap(owner, d_ptr, shape, device=-1):
+    """PyCapsule "dltensor" over device memory that `owner` (any Python object) keeps alive: the object is referenced
+    until the consumer's deleter runs."""
+    with _wrapped_lock:
+        token = _wrapped_next[0]
+        _wrapped_next[0] += 1
+        del _released[:]
+
+    def _release(_ctx, token=token):
+        with _wrapped_lock:
+            _released.append(_wrapped.pop(token, None))
+
+    cb = _RELEASE_T(_release)
+    with _wrapped_lock:
+        _wrapped[token] = (owner, cb)
+    shp = (ctypes.c_int64 * len(shape))(*[int(v) for v in shape])
+    dl = ctypes.c_void_p()
+    try:
+        check(_lib.lib().scf_dlpack_wrap(d_ptr, int(device), shp, len(shape), ctypes.cast(cb, ctypes.c_void_p), None,
+                                         ctypes.byref(dl)))
+    except Exception:
+        _release(None)
+        raise
+    return _make_capsule(dl.value)
+
+
 def get_plan(**kw):
     """Plan cached by the VALUE of its configuration (custom banks are never cached)."""
     if kw.get('custom_bank') is not None:

@@ -12,5 +12,6 @@ F="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -
 nvcc $F -c $src/scfeat_kernels.cu -o /tmp/scf_$name/k.o
 nvcc $F -c $src/scfeat_host.cu -o /tmp/scf_$name/h.o
 nvcc $F -c $src/scfeat_post.cu -o /tmp/scf_$name/p.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libscfeat_$name.so /tmp/scf_$name/k.o /tmp/scf_$name/h.o /tmp/scf_$name/p.o -ldl
+nvcc $F -c $src/scfeat_ingest.cu -o /tmp/scf_$name/i.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libscfeat_$name.so /tmp/scf_$name/k.o /tmp/scf_$name/h.o /tmp/scf_$name/p.o /tmp/scf_$name/i.o -ldl -lpthread
 echo $out/libscfeat_$name.so
