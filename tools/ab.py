@@ -43,13 +43,25 @@ for rep in range(6):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); plan.extract_device(huge.data_ptr(), 49152, 16000, hout.data_ptr(), stream=st.cuda_stream); e1.record(); torch.cuda.synchronize()
     hb = min(hb, e0.elapsed_time(e1))
-print('%-28s  512-batch %.2f us/step = %.2f M clips/s (one output buffer: %.2f) | 8192 clips %.1f us = %.2f M clips/s | 49152 clips %.2f M clips/s' % (
+ref_path = os.environ.get('AB_REF', '/tmp/ab_ref.npy')
+first = out[0].cpu().numpy()
+if os.path.exists(ref_path):
+    ref = np.load(ref_path)
+    d = np.abs(first - ref).max() / np.abs(ref).max()
+    note = 'bit-exact vs first lib' if (first == ref).all() else 'max|diff|/max|ref| vs first lib = %.2e' % d
+else:
+    np.save(ref_path, first)
+    note = 'reference output saved'
+print('%-28s  512-batch %.2f us/step = %.2f M clips/s (one output buffer: %.2f) | 8192 clips %.1f us = %.2f M clips/s | 49152 clips %.2f M clips/s | %s' % (
     os.path.basename(os.environ.get('SCFEAT_LIB', 'product')), best * 1e3, 512 / best / 1e3, 512 / same / 1e3, bb * 1e3, 8192 / bb / 1e3,
-    49152 / hb / 1e3))
+    49152 / hb / 1e3, note))
 '''
 
+rounds = int(os.environ.get('AB_ROUNDS', '2'))
 libs = sys.argv[1:] or [None]
-for rnd in range(2):
+if os.path.exists(os.environ.get('AB_REF', '/tmp/ab_ref.npy')):
+    os.remove(os.environ.get('AB_REF', '/tmp/ab_ref.npy'))
+for rnd in range(rounds):
     for lib in libs:
         env = dict(os.environ)
         if lib:
