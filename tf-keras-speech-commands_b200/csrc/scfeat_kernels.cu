@@ -428,6 +428,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     };
     if (tile_first < n_tiles) prefetch(gp0, clip0, q0);
     __syncthreads();          // mbarrier init + zeroed s_logq pad rows visible (the only CTA-wide barrier)
+#ifdef SCF_ABL_TEAMS         // scaling experiment (profiles/r02_regular_bank_tma_staging.log): only the first n teams of a CTA work
+    if (team >= SCF_ABL_TEAMS) return;
+#endif
 
     for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
         const uint32_t pair0 = tile * geo::PPT;
@@ -1014,12 +1017,21 @@ static cudaError_t launch_extract_r(bool is_f32, bool fast, const KParams& p, in
 cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms,
                            cudaStream_t st, size_t smem)
 {
+#ifdef SCF_VARIANT_BUILD      // tuning builds (tools/build_variant.sh): only the params.json fast-path kernels
+    if (r == 32 && !is_f32 && fast) {
+        const int v = variant_for_r<32>(p);
+        if (v == 3) return launch_one<32, int16_t, true, 3, true>(p, n_tiles, num_sms, st, smem);
+        if (v == 1) return launch_one<32, int16_t, true, 1, true>(p, n_tiles, num_sms, st, smem);
+    }
+    return cudaErrorInvalidValue;
+#else
     switch (r) {
         case 32: return launch_extract_r<32>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         case 16: return launch_extract_r<16>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         case 8: return launch_extract_r<8>(is_f32, fast, p, n_tiles, num_sms, st, smem);
         default: return cudaErrorInvalidValue;
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
