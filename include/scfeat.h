@@ -91,6 +91,8 @@ typedef struct scf_config {
     int32_t device;          /* CUDA device ordinal, -1 = current                        */
     int32_t delta;           /* scf_delta_kind (pr.use_delta -> SCF_DELTA_DIFF)          default NONE  */
     const double* custom_bank; /* SCF_BANK_CUSTOM only                                   */
+    float   bank_low_hz;     /* SCF_BANK_BARK_REF: low_freq / high_freq of bark_filterbanks (common/bark_feature.py:93,  */
+    float   bank_high_hz;    /*   104-105); 0 = not given -> 0 Hz / sample_rate / 2 like the reference's `x or default`    */
 } scf_config;
 
 typedef struct scf_plan scf_plan;

@@ -9,6 +9,8 @@ What is real reference output and what is oracle output is recorded per key:
   * ref_bark.npz         outputs of the UNMODIFIED /root/reference/common/bark_feature.py
                          (imported with a stub ``librosa`` -- only its __main__ uses librosa):
                          power_spec, bark_filterbanks, bark_spec, bfcc_spec
+  * ref_bark_edges.npz   bark_filterbanks of the same unmodified file with low_freq / high_freq given
+                         (written by bark_edges(); `python tests/golden/make_golden.py edges` makes only this one)
   * ref_mfcc_cpp.npz     outputs of the reference's C++ twin inference/tflite/mfcc.h compiled into
                          oracle/_ref/libref_mfcc.so (float32 I/O, double inside)
   * oracle_mfcc.npz      float64 output of oracle/sonopy.py (the restatement of un-vendored sonopy)
@@ -58,7 +60,22 @@ def cpp_mfcc(lib, audio_f32, sr, W, H, nfft, ncoef, nfilt, pre=0):
     return out
 
 
+EDGE_CASES = [(20, 512, 300, 6000, 'constant'), (24, 1024, 100, None, 'ascendant'), (26, 512, 0, 4000, 'descendant'),
+              (13, 1024, 50.5, 7600, 'constant')]
+
+
+def bark_edges():
+    """bark_filterbanks(low_freq, high_freq) of the unmodified common/bark_feature.py:93-136."""
+    rb = load_real_bark()
+    out = {}
+    for nf, nfft, lo, hi, scale in EDGE_CASES:
+        out['bank_%d_%d_%s_%s_%s' % (nf, nfft, lo, hi, scale)] = rb.bark_filterbanks(
+            nfilts=nf, nfft=nfft, sample_rate=16000, low_freq=lo, high_freq=hi, scale=scale)
+    np.savez_compressed(os.path.join(HERE, 'ref_bark_edges.npz'), **out)
+
+
 def main():
+    bark_edges()
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(REF, 'example/*.wav')))
     pcm = np.stack([pipeline.read_wav_int16(os.path.join(REF, 'example', n + '.wav'))[0] for n in names])
     assert pcm.shape == (8, 16000) and pcm.dtype == np.int16
@@ -136,7 +153,10 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] == ['edges']:
+        bark_edges()
+    else:
+        main()
 
 
 def load_reference_postprocess():

@@ -125,6 +125,28 @@ def test_bank_too_dense_for_shared_memory_is_rejected():
         _lib.bank_apply_tasks(np.ones(129), np.ones(129), n_fft=256, n_filt=64, bank=_lib.BANK_BARK_REF)
 
 
+@pytest.mark.parametrize('nf,nfft,lo,hi,scale', [(20, 512, 300, 6000, 'constant'), (24, 1024, 100, None, 'ascendant'),
+                                                 (26, 512, 0, 4000, 'descendant'), (13, 1024, 50.5, 7600, 'constant')])
+def test_bark_bank_band_edges_equal_reference_file(nf, nfft, lo, hi, scale):
+    """bark_filterbanks(low_freq, high_freq) (common/bark_feature.py:93,104-105) against the unmodified reference file
+    (tests/golden/make_golden.py bark_edges) and against the oracle."""
+    ref = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_bark_edges.npz'))
+    want = ref['bank_%d_%d_%s_%s_%s' % (nf, nfft, lo, hi, scale)]
+    got = scfeat.bark_feature.bark_filterbanks(nfilts=nf, nfft=nfft, sample_rate=16000, low_freq=lo, high_freq=hi, scale=scale)
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(obark.bark_filterbanks(nf, nfft, 16000, lo, hi, scale), want, rtol=1e-10, atol=1e-13)
+    assert (got != 0).sum() > 0
+
+
+def test_bark_bank_past_the_last_column_is_dropped_not_an_error():
+    # the reference maps bins with nfft = 512 whatever the bank width is: with nfft = 256 its loop runs past column 128
+    # and raises IndexError (even with the default band edges); the library keeps the columns that exist
+    bank = scfeat.bark_feature.bark_filterbanks(nfilts=13, nfft=256, sample_rate=16000)
+    assert bank.shape == (13, 129) and np.isfinite(bank).all() and (bank != 0).any()
+    with pytest.raises(_lib.ScfError):
+        _lib.build_bank(n_fft=512, n_filt=20, bank=_lib.BANK_BARK_REF, bank_low_hz=4000.0, bank_high_hz=1000.0)
+
+
 def test_bark_scale_helpers_match_oracle():
     f = np.array([0.0, 100.0, 1000.0, 7999.0])
     np.testing.assert_array_equal(scfeat.bark_feature.hz2bark(f), obark.hz2bark(f))
@@ -168,8 +190,8 @@ def test_bad_config_is_rejected():
     assert b'n_fft' in _lib.lib().scf_last_error()
     with pytest.raises(ValueError):
         scfeat.data_utils.vectorize_raw(np.zeros(0, np.float32))
-    with pytest.raises(ValueError):
-        scfeat.bark_feature.bark_filterbanks(nfilts=20, nfft=512, sample_rate=16000, low_freq=300)
+    with pytest.raises(scfeat.ScfError):          # band edges in the wrong order
+        scfeat.bark_feature.bark_filterbanks(nfilts=20, nfft=512, sample_rate=16000, low_freq=3000, high_freq=300)
 
 
 def test_short_audio_frame_count():

@@ -56,6 +56,7 @@ class Config(ctypes.Structure):
         ('bank', ctypes.c_int32), ('bank_scale', ctypes.c_int32), ('output', ctypes.c_int32),
         ('window_fn', ctypes.c_int32), ('preemph_alpha', ctypes.c_float), ('pcm_scale', ctypes.c_float),
         ('device', ctypes.c_int32), ('delta', ctypes.c_int32), ('custom_bank', ctypes.c_void_p),
+        ('bank_low_hz', ctypes.c_float), ('bank_high_hz', ctypes.c_float),
     ]
 
 
@@ -154,7 +155,8 @@ def check(rc):
 
 def make_config(sample_rate=16000, window=1024, hop=512, n_fft=1024, n_filt=20, n_coeffs=20,
                 bank=BANK_MEL_SONOPY, bank_scale='constant', output=OUT_CEPSTRUM, window_fn='rect',
-                preemph_alpha=0.0, pcm_scale=1.0 / 32768.0, device=-1, custom_bank=None, delta=None):
+                preemph_alpha=0.0, pcm_scale=1.0 / 32768.0, device=-1, custom_bank=None, delta=None,
+                bank_low_hz=0.0, bank_high_hz=0.0):
     c = Config()
     check(lib().scf_config_default(ctypes.byref(c)))
     c.sample_rate, c.window, c.hop, c.n_fft = int(sample_rate), int(window), int(hop), int(n_fft)
@@ -162,6 +164,7 @@ def make_config(sample_rate=16000, window=1024, hop=512, n_fft=1024, n_filt=20, 
     c.bank, c.bank_scale, c.output = int(bank), SCALE[bank_scale], int(output)
     c.window_fn, c.preemph_alpha, c.pcm_scale, c.device = WIN[window_fn], float(preemph_alpha), float(pcm_scale), int(device)
     c.delta = DELTA[delta]
+    c.bank_low_hz, c.bank_high_hz = float(bank_low_hz or 0.0), float(bank_high_hz or 0.0)
     keep = None
     if custom_bank is not None:
         keep = np.ascontiguousarray(custom_bank, dtype=np.float64)

@@ -64,11 +64,12 @@ def Fm(fb, fc):
 
 @lru_cache()
 def bark_filterbanks(nfilts=20, nfft=512, sample_rate=16000, low_freq=0, high_freq=None, scale="constant"):
-    """Bark filterbank [nfilts, nfft/2+1] as libscfeat builds it (float64, host).  Only the reference's
-    own call shape (low_freq=0, high_freq=None -> sample_rate/2) is supported."""
-    if (low_freq or 0) != 0 or (high_freq is not None and high_freq != sample_rate / 2):
-        raise ValueError('only low_freq=0 / high_freq=None (the reference call shape) is supported')
-    return _lib.build_bank(sample_rate=sample_rate, n_fft=nfft, n_filt=nfilts, bank=BANK_BARK_REF, bank_scale=scale)
+    """Bark filterbank [nfilts, nfft/2+1] as libscfeat builds it (float64, host); same arguments as
+    common/bark_feature.py:93 -- `low_freq or 0`, `high_freq or sample_rate / 2` (:104-105).  Bins past the last
+    column (high_freq above the 8 kHz the reference's fixed bin mapping covers) are dropped where the reference
+    raises IndexError."""
+    return _lib.build_bank(sample_rate=sample_rate, n_fft=nfft, n_filt=nfilts, bank=BANK_BARK_REF, bank_scale=scale,
+                           bank_low_hz=float(low_freq or 0), bank_high_hz=float(high_freq or 0))
 
 
 def _run(audio, out_kind, sample_rate, window_size, hop_size, fft_size, **kw):

@@ -76,15 +76,18 @@ static void build_mel_sonopy(int sample_rate, int n_filt, int n_bins, std::vecto
 
 // common/bark_feature.py:92-136.  bark2fft / fft2bark are used with their DEFAULT nfft=512 and
 // sample_rate=16000 (bark_feature.py:112,134 pass neither) -- reproduced on purpose.
-static void build_bark_ref(int sample_rate, int n_filt, int n_bins, int scale, std::vector<double>& bank)
+static void build_bark_ref(int sample_rate, int n_filt, int n_bins, int scale, double low_hz, double high_hz,
+                           std::vector<double>& bank)
 {
     const double map_nfft = 512.0, map_rate = 16000.0;
     auto hz2bark = [](double f) { return 6.0 * asinh(f / 600.0); };             // :27-29
     auto bark2hz = [](double b) { return 600.0 * sinh(b / 6.0); };              // :32-34
     auto fft2bark = [&](double k) { return hz2bark((k * map_rate) / (map_nfft + 1.0)); };     // :47-49
     auto bark2fft = [&](double b) { return (map_nfft + 1.0) * bark2hz(b) / map_rate; };       // :52-56
-    const double high = (double)sample_rate / 2.0;
-    std::vector<double> pts = linspace(hz2bark(0.0), hz2bark(high), n_filt + 4);
+    // band edges: `high_freq or sample_rate / 2`, `low_freq or 0` (:104-105) -- 0 means "not given"
+    const double high = high_hz > 0.0 ? high_hz : (double)sample_rate / 2.0;
+    const double low = low_hz > 0.0 ? low_hz : 0.0;
+    std::vector<double> pts = linspace(hz2bark(low), hz2bark(high), n_filt + 4);
     std::vector<long> bins(n_filt + 4);
     for (int i = 0; i < n_filt + 4; ++i) bins[i] = (long)floor(bark2fft(pts[i]));
     bank.assign((size_t)n_filt * n_bins, 0.0);
@@ -98,7 +101,9 @@ static void build_bark_ref(int sample_rate, int n_filt, int n_bins, int scale, s
             c = c * (c < 1 ? 1.0 : 0.0) + (c > 1 ? 1.0 : 0.0);
         }
         const double fc = pts[i + 2];
-        for (long j = bins[i]; j < bins[i + 4] && j < n_bins; ++j) {
+        // (the reference indexes fbank[i, j] for every j of the range and raises IndexError past the last column --
+        //  only reachable with high_freq above the 8 kHz the fixed bin mapping covers; such bins are dropped here)
+        for (long j = std::max(0L, bins[i]); j < bins[i + 4] && j < n_bins; ++j) {
             const double fb = fft2bark((double)j);
             double v = 0.0;                                                      // Fm, :59-72
             if (fc - 2.5 <= fb && fb <= fc - 0.5) v = pow(10.0, 2.5 * (fb - fc + 0.5));
@@ -116,6 +121,8 @@ static int check_config(const scf_config* c)
         return fail(SCF_ERR_INVALID, "n_fft must be 256, 512 or 1024");
     if (c->window < 1 || c->hop < 1) return fail(SCF_ERR_INVALID, "window and hop must be positive");
     if (c->sample_rate < 1) return fail(SCF_ERR_INVALID, "sample_rate must be positive");
+    if (!(c->bank_low_hz >= 0.f) || !(c->bank_high_hz >= 0.f) || (c->bank_high_hz > 0.f && c->bank_high_hz <= c->bank_low_hz))
+        return fail(SCF_ERR_INVALID, "bank_low_hz / bank_high_hz must be 0 (default) or 0 <= low < high");
     if (c->output < SCF_OUT_POWER || c->output > SCF_OUT_CEPSTRUM) return fail(SCF_ERR_INVALID, "bad output kind");
     if (c->output != SCF_OUT_POWER) {
         if (c->n_filt < 1 || c->n_filt > 64) return fail(SCF_ERR_INVALID, "n_filt must be in 1..64");
@@ -133,7 +140,7 @@ static int build_bank(const scf_config* c, std::vector<double>& bank)
 {
     const int n_bins = c->n_fft / 2 + 1;
     if (c->bank == SCF_BANK_MEL_SONOPY) build_mel_sonopy(c->sample_rate, c->n_filt, n_bins, bank);
-    else if (c->bank == SCF_BANK_BARK_REF) build_bark_ref(c->sample_rate, c->n_filt, n_bins, c->bank_scale, bank);
+    else if (c->bank == SCF_BANK_BARK_REF) build_bark_ref(c->sample_rate, c->n_filt, n_bins, c->bank_scale, c->bank_low_hz, c->bank_high_hz, bank);
     else bank.assign(c->custom_bank, c->custom_bank + (size_t)c->n_filt * n_bins);
     return SCF_OK;
 }
