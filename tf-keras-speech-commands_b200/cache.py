@@ -63,7 +63,7 @@ def load_wav_batch(paths, n_threads=None):
     return pcm, lengths
 
 
-def ingest_wavs(paths, batch=4096, n_threads=None, out=None):
+def ingest_wavs(paths, batch=512, n_threads=None, out=None):
     """wav files -> float32 [n, n_features, feature_size] through the pipelined native path (scf_ingest_wavs): reader
     threads fill pinned staging slots while earlier slots are uploaded, transformed and downloaded.  Returns
     (features, lengths)."""
@@ -85,7 +85,7 @@ def ingest_wavs(paths, batch=4096, n_threads=None, out=None):
     return out, lengths
 
 
-def extract_features(audio_path, class_names, batch=4096):
+def extract_features(audio_path, class_names, batch=512):
     """wav tree -> list of {'data': (n_features, feature_size, 1) float32, 'label': class} like data.py:30-46, through
     the pipelined ingest (one file of zero length gives all-silence rows, as the reference's front padding does)."""
     sample_list = get_sample_list(audio_path, class_names)
@@ -143,7 +143,7 @@ def labels_of(sample_list, class_names):
     return np.asarray([class_names.index(s['word'].lower()) for s in sample_list], dtype=np.int64)
 
 
-def get_dataset_device(dataset_path, class_names, batch=4096, device=-1):
+def get_dataset_device(dataset_path, class_names, batch=512, device=-1):
     """The training set straight from the wav tree to the framework, without the 105k one-clip .npy files of
     data.py:49-68 and :97-114: reader threads + pinned staging feed the extraction kernels (scf_ingest_wavs_device), the
     features stay on the GPU.  Returns (x, y): x = DLPack capsule "dltensor", float32 [N, n_features, feature_size, 1]
