@@ -24,7 +24,7 @@ def audio_of(pcm):
     return pcm.astype(np.float32) / 32768.0
 
 
-def assert_cepstrum_close(got, want):
+def assert_cepstrum_close(got, want, elementwise=True):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape
     scale = np.abs(want).reshape(want.shape[0], -1).max(axis=1) if want.ndim == 3 else np.abs(want).max()
@@ -34,7 +34,8 @@ def assert_cepstrum_close(got, want):
         assert (err <= CEP_REL * scale).all(), (err / scale).max()
     else:
         assert err.max() <= CEP_REL * scale, err.max() / scale
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    if elementwise:
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
 
 
 def assert_log_close(got, want):
@@ -251,6 +252,69 @@ def test_preemphasis_and_hamming_vs_oracle(example_pcm):
     plan = scfeat.get_plan(window=W, hop=H, n_fft=1024, n_filt=20, n_coeffs=20, preemph_alpha=0.95, window_fn='hamming')
     assert_cepstrum_close(plan.extract_host(pcm[2]), want)
     assert_cepstrum_close(plan.extract_host(audio_of(pcm[2])), want)
+
+
+def _front_end_oracle(audio, alpha, window_fn, W, H, n_fft, n_filt, n_coeffs):
+    """float64: x[n] - alpha x[n-1] (x[-1] := 0) over the whole clip, frames times the window (denominator W - 1,
+    mfcc.h:394-410), then the sonopy restatement's power -> mel -> log -> DCT with c0 := log energy."""
+    from scipy.fftpack import dct
+    a = np.asarray(audio, dtype=np.float64)
+    pre = a.copy()
+    pre[1:] -= np.float64(np.float32(alpha)) * a[:-1]
+    n = np.arange(W)
+    win = {'rect': np.ones(W), 'hamming': 0.54 - 0.46 * np.cos(2 * np.pi * n / (W - 1)),
+           'hann': 0.5 - 0.5 * np.cos(2 * np.pi * n / (W - 1))}[window_fn]
+    frames = osonopy.frames_of(pre, W, H) * win
+    spec = np.fft.rfft(frames, n=n_fft)
+    powers = (spec.real ** 2 + spec.imag ** 2) / n_fft
+    mels = osonopy.safe_log(powers @ osonopy.filterbanks(16000, n_filt, n_fft // 2 + 1).T)
+    out = dct(mels, norm='ortho')[:, :n_coeffs]
+    out[:, 0] = osonopy.safe_log(powers.sum(1))
+    return out
+
+
+@pytest.mark.parametrize('n_fft, alpha, window_fn, nf', [(1024, 0.95, 'hamming', 20), (1024, 0.97, 'rect', 20),
+                                                         (1024, 0.0, 'hann', 20), (512, 0.95, 'hamming', 20),
+                                                         (256, 0.95, 'hamming', 10)])
+def test_fused_front_end_on_the_fast_kernels(example_pcm, n_fft, alpha, window_fn, nf):
+    """Pre-emphasis and / or a window on the fast geometry (window = n_fft, hop = n_fft / 2) run inside the fast loader
+    (mfcc.h:394-410): small and large jobs (all kernel variants), int16 and float input, short clips padded in front,
+    an odd number of frames -- against the float64 oracle, and against the generic loader on the same input."""
+    _, pcm = example_pcm
+    W, H = n_fft, n_fft // 2
+    # (n_fft = 256 with 10 filters: with 20, filter 0 of sonopy's grid is bin 0 alone, and the DC term of a
+    #  pre-emphasised, windowed frame is a sum of 256 cancelling values -- 1e-12 of the frame energy, which fp32 cannot
+    #  resolve: |diff| up to 2e-2 in that one log band, the same bit for bit through the generic loader)
+    plan = scfeat.get_plan(window=W, hop=H, n_fft=n_fft, n_filt=nf, n_coeffs=nf, preemph_alpha=alpha, window_fn=window_fn)
+    want8 = np.stack([_front_end_oracle(a, alpha, window_fn, W, H, n_fft, nf, nf) for a in audio_of(pcm)])
+    assert_cepstrum_close(plan.extract_host(pcm), want8)
+    assert_cepstrum_close(plan.extract_host(audio_of(pcm)), want8)
+    # a large job (three-team kernels) of rolled copies: every clip differs, the oracle is evaluated on a sample
+    n = 1664
+    rng = np.random.default_rng(5)
+    shifts = rng.integers(0, 16000, size=n)
+    clips = np.stack([np.roll(pcm[i % 8], shifts[i]) for i in range(n)])
+    got = plan.extract_host(clips)
+    for i in list(range(0, n, 97)) + [n - 1]:
+        assert_cepstrum_close(got[i], _front_end_oracle(audio_of(clips[i]), alpha, window_fn, W, H, n_fft, nf, nf))
+    generic = plan.extract_host(clips, lengths=np.full(n, 16000, np.int32), pad=scfeat.plan.PAD_NONE)
+    np.testing.assert_array_equal(got, generic)          # the generic loader: same arithmetic, bit for bit
+    # short clips, zero-padded in front (common/data_utils.py:77-80), incl. every alignment class of the first sample
+    m = 72
+    lengths = rng.integers(0, 16001, size=m).astype(np.int32)
+    lengths[:10] = [16000, 0, 1, 2, 15999, 16000 - H, 16000 - H - 1, 16000 - W, 16000 - W - 1, 16000 - W + 1]
+    got = plan.extract_host(clips[:m], lengths=lengths)
+    for i in range(m):
+        padded = np.concatenate([np.zeros(16000 - lengths[i], np.float32), audio_of(clips[i][:lengths[i]])])
+        assert_cepstrum_close(got[i], _front_end_oracle(padded, alpha, window_fn, W, H, n_fft, nf, nf))
+    # odd frame count (the last pair of a clip has no second frame), and the generic loader on the same samples
+    L = W + 8 * H                                   # 9 frames
+    got = plan.extract_host(clips[:40, :L])
+    assert got.shape[1] == 9
+    for i in range(0, 40, 7):
+        assert_cepstrum_close(got[i], _front_end_oracle(audio_of(clips[i, :L]), alpha, window_fn, W, H, n_fft, nf, nf))
+    generic = plan.extract_host(clips[:40, :L], lengths=np.full(40, L, np.int32), pad=scfeat.plan.PAD_NONE)
+    np.testing.assert_array_equal(got, generic)          # same arithmetic, bit for bit
 
 
 def test_custom_bank_matches_builtin(example_pcm):

@@ -485,10 +485,11 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
     p->power_scale_i16 = (float)ps_i16;
 
     // analysis window over the (uncropped) window length, inference/tflite/mfcc.h:404-407
-    if (cfg->window_fn != SCF_WIN_RECT) {
+    // (pre-emphasis alone gets a table of ones: the fused fast loader always multiplies)
+    if (cfg->window_fn != SCF_WIN_RECT || cfg->preemph_alpha != 0.f) {
         const int w_eff = std::min(cfg->window, cfg->n_fft);
-        std::vector<float> win(w_eff);
-        for (int j = 0; j < w_eff; ++j) {
+        std::vector<float> win(w_eff, 1.f);
+        for (int j = 0; j < w_eff && cfg->window_fn != SCF_WIN_RECT; ++j) {
             const double c = cos(2.0 * M_PI * j / (double)(cfg->window - 1));
             win[j] = (float)(cfg->window_fn == SCF_WIN_HAMMING ? 0.54 - 0.46 * c : 0.5 - 0.5 * c);
         }
@@ -620,8 +621,9 @@ static int fill_params(const scf_plan* plan, bool is_f32, const void* d_in, int6
     const int ppt = pairs_per_tile(plan->radix_r);
     n_tiles = (kp.n_pairs + ppt - 1) / ppt;
     // the fast kernels also take short clips that are zero-padded in front (common/data_utils.py:77-80)
-    fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && (d_lengths == nullptr || pad == SCF_PAD_FRONT_ZERO) &&
-           c.preemph_alpha == 0.f && c.window_fn == SCF_WIN_RECT;
+    // ... and, with a second load per sample, pre-emphasis and an analysis window (inference/tflite/mfcc.h:394-410)
+    fast = (c.window == c.n_fft) && (c.hop * 2 == c.n_fft) && (d_lengths == nullptr || pad == SCF_PAD_FRONT_ZERO);
+    kp.fast_pre = (fast && (c.preemph_alpha != 0.f || c.window_fn != SCF_WIN_RECT)) ? 1 : 0;
     return SCF_OK;
 }
 
@@ -644,6 +646,7 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
         kp.stream = *stream_step;
         kp.out_pitch = plan->base_cols;       // `out` is the stream's own ring: base columns only
         fast = false;             // the generic loader reads concat(carry, chunk)
+        kp.fast_pre = 0;
     }
     kp.fast_path = fast ? 1 : 0;
     if (peers) {

@@ -102,7 +102,8 @@ struct KParams {
     int32_t n_out;               // cepstrum columns = min(n_filt, n_coeffs)
     int32_t frames_odd;          // frames_per_clip is odd: the last pair of a clip has no frame B
     uint32_t ppc_magic, ppc_shift;   // fast division by pairs_per_clip
-    int32_t fast_path;           // 1: window == n_fft, hop == n_fft/2, full clips, no window / pre-emphasis (FAST kernels)
+    int32_t fast_path;           // 1: window == n_fft, hop == n_fft/2, full or front-padded clips (FAST kernels)
+    int32_t fast_pre;            // ... with pre-emphasis and / or a window table fused into the loader (`win` is never NULL then)
     int32_t stream_on;           // 1: `stream` describes a streaming step (in == stream.carry_in, lengths unused)
     StreamStep stream;
 };

@@ -259,11 +259,16 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
 //              weights and the DCT matrix are read through L1 instead of shared memory to fit three CTAs;
 //   TEAMS = 3: one 768-thread CTA of three independent teams that share one table copy and synchronise through their
 //              own named barriers -- large jobs.
-template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
+// PRE (fast geometry only): pre-emphasis x[n] - alpha * x[n-1] (x[-1] := 0) and / or an analysis window fused into
+//            the loader (inference/tflite/mfcc.h:394-410): every lane also loads the sample in front of each of its
+//            samples (the same cache lines), and the window values of its positions come through L1.
+template <int R, typename InT, bool FAST, int TEAMS, bool DENSE, bool PRE>
 __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 : kCtasPerSm))
     extract_kernel(const KParams p, const uint32_t n_tiles)
 {
     static_assert(TEAMS == 1 || DENSE, "multi-team CTAs need the dense register budget");
+    static_assert(FAST || !PRE, "the generic loader has its own pre-emphasis / window code");
+    static_assert(!(PRE && DENSE), "the fused front end needs a second set of sample registers: classic variant only");
     using geo = Geo<R>;
     extern __shared__ __align__(16) float smem[];
 
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     //  * fast int16 path: from the frame energy in the epilogue -- a non-zero int16 frame has raw energy >= 0.5
     //    while its partner can leak at most ~2e-3 into it, so energy < 0.25 means "all zero";
     //  * everything else (float input, generic loader): bitwise OR of the samples + warp vote.
-    constexpr bool kEnergyZero = FAST && sizeof(InT) == 2;
+    constexpr bool kEnergyZero = FAST && sizeof(InT) == 2 && !PRE;
     constexpr bool bit_detect = !kEnergyZero;
     const InT* __restrict__ in = reinterpret_cast<const InT*>(p.in);
     const uint32_t ppc = (uint32_t)p.pairs_per_clip;
@@ -409,11 +414,31 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 dst[j] = (j >= j0 && j < n_ld) ? ld_sample(cb + (e0 - pad + lane + 32 * j)) : (RawT)0;
         }
     };
+    // PRE: prv[j] = the element in front of raw[j] (zero in front of the clip's first sample and inside the padding)
+    auto load_prev = [&](uint32_t clip, uint32_t q, RawT (&dst)[geo::NLOAD]) {
+        int pad = 0;
+        if (p.lengths != nullptr) pad = p.clip_len - min(max(__ldg(p.lengths + clip), 0), p.clip_len);
+        const int e0 = (int)q * geo::NFFT;
+        const InT* __restrict__ cb = in + (int64_t)clip * p.clip_stride;
+        const bool b_absent = p.frames_odd != 0 && q + 1 == ppc;
+        const int n_ld = b_absent ? R : geo::NLOAD;
+        if (__builtin_expect(pad <= e0 && !b_absent, 1)) {
+            const InT* __restrict__ src = cb + (e0 - pad) + lane - 1;
+            dst[0] = ld_sample_if(src, lane != 0 || e0 != pad);
+#pragma unroll
+            for (int j = 1; j < geo::NLOAD; ++j) dst[j] = ld_sample(src + 32 * j);
+        } else {
+            const int j0 = (pad - e0 - lane + 32) >> 5;       // first j with e0 + lane + 32 j - 1 >= pad
+#pragma unroll
+            for (int j = 0; j < geo::NLOAD; ++j)
+                dst[j] = ld_sample_if(cb + (e0 - pad + lane + 32 * j - 1), j >= j0 && j < n_ld);
+        }
+    };
     // classic variant: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases of
     // the current tile run (those need few registers), so the FFT stage never waits on HBM
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead;
     //  the 24-warp CTAs have no registers to spare and prefetch into L2 instead)
-    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE;
+    constexpr bool kPrefetch = FAST && sizeof(InT) == 2 && !DENSE && !PRE;   // (with PRE: 968 bytes of spills)
     auto prefetch = [&](uint32_t gp, uint32_t c_in, uint32_t q_in) {
         if constexpr (kPrefetch) {
 #pragma unroll
@@ -468,21 +493,45 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                                     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(nsrc) + lane * 128));
                             }
                         }
-                        if (bit_detect) {
-                            uint32_t o0 = 0, o1 = 0, o2 = 0;
+                        if constexpr (PRE) {
+                            // e[n] = x[n] - alpha * x[n-1] for the 1.5 frames of the pair, then both frames times the
+                            // window value of their common position n2 + 32 n1 (alpha may be 0, the window all ones)
+                            float e[geo::NLOAD];
+                            const float ma = -p.preemph;
+                            const float* __restrict__ wl = p.win + lane;
+                            // x of position n1 as soon as e[n1 + R/2] exists: never more than 64 live values
+                            auto emit = [&](int n1) {
+                                const int i = scf_bitrev(n1, geo::LOG2R);
+                                x[i] = mul2(pk(e[n1], e[n1 + R / 2]), bc(__ldg(wl + 32 * n1)));
+                                nz_a |= __float_as_uint(lo(x[i]));
+                                nz_b |= __float_as_uint(hi(x[i]));
+                            };
+                            RawT prv[geo::NLOAD];
+                            load_prev(clip, q, prv);
 #pragma unroll
-                            for (int j = 0; j < R / 2; ++j) {
-                                o0 |= nz_bits(raw[g][j]);
-                                o1 |= nz_bits(raw[g][j + R / 2]);
-                                o2 |= nz_bits(raw[g][j + R]);
+                            for (int j = 0; j < geo::NLOAD; ++j) {
+                                e[j] = fmaf(ma, to_f32(prv[j]), to_f32(raw[g][j]));
+                                if (j >= R / 2) emit(j - R / 2);
                             }
-                            nz_a = o0 | o1;
-                            nz_b = b_absent ? 0u : (o1 | o2);
-                        }
+                            nz_a &= 0x7fffffffu;                                         // (-0.0f counts as zero)
+                            nz_b = b_absent ? 0u : (nz_b & 0x7fffffffu);
+                        } else {
+                            if (bit_detect) {
+                                uint32_t o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
-                        for (int i = 0; i < R; ++i) {
-                            const int n1 = scf_bitrev(i, geo::LOG2R);
-                            x[i] = pk(to_f32(raw[g][n1]), to_f32(raw[g][n1 + R / 2]));
+                                for (int j = 0; j < R / 2; ++j) {
+                                    o0 |= nz_bits(raw[g][j]);
+                                    o1 |= nz_bits(raw[g][j + R / 2]);
+                                    o2 |= nz_bits(raw[g][j + R]);
+                                }
+                                nz_a = o0 | o1;
+                                nz_b = b_absent ? 0u : (o1 | o2);
+                            }
+#pragma unroll
+                            for (int i = 0; i < R; ++i) {
+                                const int n1 = scf_bitrev(i, geo::LOG2R);
+                                x[i] = pk(to_f32(raw[g][n1]), to_f32(raw[g][n1 + R / 2]));
+                            }
                         }
                         if (__builtin_expect(b_absent, 0)) {   // frame B does not exist: imaginary parts are zero
 #pragma unroll
@@ -905,7 +954,7 @@ template <int R>
 static int variant_for_r(const KParams& p)
 {
     static const int forced = [] { const char* e = getenv("SCFEAT_VARIANT"); return e ? atoi(e) : -1; }();
-    if (forced == 0 || !p.fast_path) return 0;                // (the generic loader needs the classic register budget)
+    if (forced == 0 || !p.fast_path || p.fast_pre) return 0;  // (the generic loader and the fused front end need the classic register budget)
     const bool fits3 = smem_bytes_rt<R, 3, true>(p) <= kSmemMaxBlock;
     const bool fits1 = R == 32 && 3 * (smem_bytes_rt<R, 1, true>(p) + kSmemReserve) <= kSmemPerSm;
     if (forced == 3 && fits3) return 3;
@@ -944,10 +993,10 @@ size_t extract_smem_limit(int r, const KParams& p)
 int pairs_per_tile(int r) { return kWarps * (32 / r); }
 int bank_groups(int r) { return kThreads / (kWarps * (32 / r)); }
 
-template <int R, typename InT, bool FAST, int TEAMS, bool DENSE>
+template <int R, typename InT, bool FAST, int TEAMS, bool DENSE, bool PRE>
 static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
 {
-    auto kern = extract_kernel<R, InT, FAST, TEAMS, DENSE>;
+    auto kern = extract_kernel<R, InT, FAST, TEAMS, DENSE, PRE>;
     // per device: the attribute call costs microseconds per launch, so it is made once per size (plans are shared
     // between threads: the bookkeeping is atomic, and setting the attribute twice is harmless)
     static std::atomic<size_t> configured[16];
@@ -985,20 +1034,28 @@ static cudaError_t launch_one(const KParams& p, int64_t n_tiles, int num_sms, cu
     return cudaGetLastError();
 }
 
+// fast geometry (the params.json kernels), with or without the fused pre-emphasis / window loader
+template <int R, typename InT, int TEAMS, bool DENSE>
+static cudaError_t launch_fast(const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st, size_t smem)
+{
+    return p.fast_pre ? launch_one<R, InT, true, TEAMS, DENSE, true>(p, n_tiles, num_sms, st, smem)
+                      : launch_one<R, InT, true, TEAMS, DENSE, false>(p, n_tiles, num_sms, st, smem);
+}
+
 template <int R, int TEAMS, bool DENSE>
 static cudaError_t launch_r(bool is_f32, bool fast, const KParams& p, int64_t n_tiles, int num_sms, cudaStream_t st,
                             size_t smem)
 {
-    if constexpr (DENSE) {        // fast path only (variant_for)
-        return is_f32 ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
-                      : launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+    if constexpr (DENSE) {        // fast path without a front end only (variant_for)
+        return is_f32 ? launch_one<R, float, true, TEAMS, DENSE, false>(p, n_tiles, num_sms, st, smem)
+                      : launch_one<R, int16_t, true, TEAMS, DENSE, false>(p, n_tiles, num_sms, st, smem);
     } else {
         if (is_f32) {
-            return fast ? launch_one<R, float, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
-                        : launch_one<R, float, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+            return fast ? launch_fast<R, float, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                        : launch_one<R, float, false, TEAMS, DENSE, false>(p, n_tiles, num_sms, st, smem);
         }
-        return fast ? launch_one<R, int16_t, true, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
-                    : launch_one<R, int16_t, false, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem);
+        return fast ? launch_fast<R, int16_t, TEAMS, DENSE>(p, n_tiles, num_sms, st, smem)
+                    : launch_one<R, int16_t, false, TEAMS, DENSE, false>(p, n_tiles, num_sms, st, smem);
     }
 }
 
@@ -1020,8 +1077,8 @@ cudaError_t launch_extract(int r, bool is_f32, bool fast, const KParams& p, int6
 #ifdef SCF_VARIANT_BUILD      // tuning builds (tools/build_variant.sh): only the params.json fast-path kernels
     if (r == 32 && !is_f32 && fast) {
         const int v = variant_for_r<32>(p);
-        if (v == 3) return launch_one<32, int16_t, true, 3, true>(p, n_tiles, num_sms, st, smem);
-        if (v == 1) return launch_one<32, int16_t, true, 1, true>(p, n_tiles, num_sms, st, smem);
+        if (v == 3) return launch_one<32, int16_t, true, 3, true, false>(p, n_tiles, num_sms, st, smem);
+        if (v == 1) return launch_one<32, int16_t, true, 1, true, false>(p, n_tiles, num_sms, st, smem);
     }
     return cudaErrorInvalidValue;
 #else

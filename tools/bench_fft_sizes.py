@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Throughput of the fast path for the three FFT sizes (window = n_fft, hop = n_fft / 2), device-resident int16 input:
 MFCC 20/20 and the reference's Bark defaults (26 filters, 13 coefficients) -- and of the generic loader on sonopy's
-default geometry (window 160, hop 80, n_fft 512) and on params.json with pre-emphasis + Hamming.
+default geometry (window 160, hop 80, n_fft 512), and of params.json with pre-emphasis + Hamming (fused into the fast loader).
 Usage: python tools/bench_fft_sizes.py"""
 import os
 import sys
@@ -50,7 +50,7 @@ for name, kw in (('sonopy defaults: window 160 hop 80 n_fft 512, 20/13', dict(wi
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     assert torch.isfinite(out).all()
-    print('generic: %-52s %6.2f G frames/s  %6.2f M clips/s' % (name, n * frames / best / 1e6, n / best / 1e3))
+    print('other geometry / front end: %-40s %6.2f G frames/s  %6.2f M clips/s' % (name, n * frames / best / 1e6, n / best / 1e3))
 
 # ragged batch: per-clip lengths with front padding (common/data_utils.py:77-80); ~10 % of Speech Commands clips are short
 plan = scfeat.get_plan()
