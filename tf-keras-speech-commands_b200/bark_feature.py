@@ -3,6 +3,10 @@
 power_spec :85-89, bark_filterbanks :92-136, bark_spec :139-153, bfcc_spec :156-175 and the scale
 helpers :16-72.  The scale helpers and Fm are host-side scalar functions (as in the reference); every
 per-frame quantity comes from libscfeat's kernels.  Results are float32.
+
+Input convention: an int16 array is taken as PCM and scaled by 1/32768 inside the loader (the reference's callers
+always convert first, common/data_utils.py:21); the reference functions themselves would compute on the raw integer
+values -- pass ``pcm.astype(np.float32)`` for that.  Other dtypes are converted to float32 and used as is.
 """
 from functools import lru_cache
 

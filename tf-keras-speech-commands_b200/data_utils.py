@@ -55,7 +55,8 @@ def add_deltas(features, kind='diff'):
 
 
 def vectorize_raw(audio):
-    """turns audio into feature vectors, without clipping for length"""
+    """turns audio into feature vectors, without clipping for length
+    (int16 input = PCM, scaled by 1/32768 in the loader like buffer_to_audio; float input is used as is)"""
     if len(audio) == 0:
         raise ValueError('Cannot vectorize empty audio!')      # the reference raises an undefined name here
     a = np.asarray(audio)

@@ -4,6 +4,12 @@ Call shapes are fixed by the reference's call sites: common/data_utils.py:69,
 tools/misc/plot_spectrogram.py:25,28, tools/audio_process/mfcc_feature.py:44.  Every numeric result
 comes from libscfeat's CUDA kernels; results are float32 (the reference computes float64 and stores
 float32, classifier/data.py:67).  There is no CPU fallback.
+
+Input convention (one deliberate difference from sonopy): an **int16** array is taken as PCM and scaled by 1/32768 inside
+the loader -- the result equals ``mfcc_spec(buffer_to_audio(pcm.tobytes()), ...)``, the only way the reference ever
+feeds these functions (common/data_utils.py:21,69).  sonopy itself would compute on the raw integer values (features
+offset by log(32768^2) in every log band); pass ``pcm.astype(np.float32)`` to get exactly that.  Every other dtype is
+converted to float32 and used as is.
 """
 from functools import lru_cache
 
