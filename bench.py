@@ -271,9 +271,10 @@ def run_reference(args):
 def run_config3(plan, rank, world, local_rank, dist, st):
     """BASELINE configs[2]: the 105,829-clip corpus sharded over the ranks (rank r owns clips [r*ceil(N/R), ...)), every
     rank ends up with the whole [N, 30, 20] feature cache.  Times (CUDA events, best of 5, max over ranks) the
-    extraction alone, the fused extraction + all-gather (the kernel epilogue stores every row into all ranks' caches
-    through NVLink peer mappings, scf_extract_i16_gather) and extraction followed by ncclAllGather; checks that every
-    rank's cache equals what the owning rank computes locally, bit for bit.  Returns the "config3" object (rank 0)."""
+    extraction alone, the fused extraction + all-gather (the kernel epilogue stores every row into all ranks' caches:
+    through CUDA-IPC peer mappings, scf_extract_i16_gather, and -- where the fabric has NVLink SHARP multicast -- with one
+    multimem.st to a multicast mapping, scf_extract_i16_gather_multicast) and extraction followed by ncclAllGather;
+    checks that every rank's cache equals what the owning rank computes locally, bit for bit.  Returns the "config3" object (rank 0)."""
     import numpy as np
     import torch
     from scfeat.dist import FeatureCacheGather, shard_range
@@ -284,6 +285,20 @@ def run_config3(plan, rank, world, local_rank, dist, st):
     d_pcm = torch.randint(-32768, 32768, (max(count, 1), CLIP_LEN), dtype=torch.int16, device='cuda', generator=g)
     group = dist.group.WORLD if dist is not None else None
     cache = FeatureCacheGather(plan, n, CLIP_LEN, world, rank, local_rank, group=group)
+    # second cache in torch symmetric memory with a multicast mapping: the epilogue then issues ONE multimem.st per row
+    # segment and the NVSwitch replicates it (every rank must get the mapping, or none uses it)
+    mcache, mc_note = None, 'single GPU'
+    if dist is not None:
+        try:
+            mcache = FeatureCacheGather(plan, n, CLIP_LEN, world, rank, local_rank, group=group, multicast=True)
+            mc_note = None
+        except Exception as e:      # no multicast on this fabric / torch build
+            mc_note = '%s: %s' % (type(e).__name__, str(e)[:160])
+        have = torch.tensor([1 if mcache is not None else 0], device='cuda')
+        dist.all_reduce(have, op=dist.ReduceOp.MIN)
+        if int(have[0]) == 0 and mcache is not None:
+            mcache.close()
+            mcache, mc_note = None, 'another rank has no multicast mapping'
 
     def sync():
         if dist is not None:
@@ -309,9 +324,6 @@ def run_config3(plan, rank, world, local_rank, dist, st):
         local_out = torch.empty((per, FRAMES, COLS), dtype=torch.float32, device='cuda')
         full = torch.empty((world * per, FRAMES, COLS), dtype=torch.float32, device='cuda')
         # ---- correctness: my cache's block of every rank equals what that rank computes locally -----------------
-        sync()
-        cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream)
-        sync()
         local_out.zero_()
         plan.extract_device(d_pcm.data_ptr(), count, CLIP_LEN, local_out.data_ptr(), stream=st.cuda_stream)
         torch.cuda.synchronize()
@@ -320,15 +332,28 @@ def run_config3(plan, rank, world, local_rank, dist, st):
         else:
             full.copy_(local_out)
         torch.cuda.synchronize()
-        got = cache.to_host()
-        ok = bool(np.array_equal(got, full[:n].cpu().numpy())) and bool(np.isfinite(got).all())
-        flag = torch.tensor([1 if ok else 0], device='cuda')
+        want = full[:n].cpu().numpy()
+        flag = torch.tensor([1], device='cuda')
+        for c in (cache, mcache):
+            if c is None:
+                continue
+            sync()
+            c.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream)
+            sync()
+            got = c.to_host()
+            if not (np.array_equal(got, want) and np.isfinite(got).all()):
+                flag.zero_()
+            del got
+        del want
         if dist is not None:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        del got
         # ---- timings --------------------------------------------------------------------------------------------
         t_extract = timed(lambda: plan.extract_device(d_pcm.data_ptr(), count, CLIP_LEN, local_out.data_ptr(), stream=st.cuda_stream))
-        t_fused = timed(lambda: cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream))
+        t_peer = timed(lambda: cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream))
+        t_mc = None
+        if mcache is not None:
+            t_mc = timed(lambda: mcache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream))
+        t_fused = t_peer if t_mc is None else min(t_peer, t_mc)
         t_nccl = None
         if dist is not None:
             def nccl_path():
@@ -339,6 +364,8 @@ def run_config3(plan, rank, world, local_rank, dist, st):
         t_single = None
         del full, local_out, d_pcm
         cache.close()
+        if mcache is not None:
+            mcache.close()
         torch.cuda.empty_cache()
         if world == 1:
             t_single = t_extract
@@ -367,6 +394,10 @@ def run_config3(plan, rank, world, local_rank, dist, st):
                     '[N, 30, 20] feature cache' % (n, world, per),
         'ok_bit_exact_on_every_rank': bool(int(flag[0])),
         'extract_only_ms': t_extract, 'fused_extract_gather_ms': t_fused, 'extract_plus_nccl_allgather_ms': t_nccl,
+        'fused_peer_stores_ms': t_peer, 'fused_multicast_ms': t_mc,
+        'fused_path': 'multimem.st to the multicast address of a torch symmetric-memory cache' if (t_mc is not None and t_mc <= t_peer)
+                      else '16-byte st.global to every rank\'s CUDA-IPC mapping',
+        'multicast_unavailable': mc_note,
         'extract_only_clips_per_s': n / (t_extract * 1e-3), 'fused_clips_per_s': n / (t_fused * 1e-3),
         'single_gpu_whole_corpus_ms': t_single,
         'efficiency_extract_only_vs_1gpu': t_single / (world * t_extract),

@@ -280,6 +280,15 @@ int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n
                            int32_t clip_len, float* const* d_peer_out, int32_t world, int32_t rank,
                            int64_t clips_per_rank, void* cuda_stream);
 
+/* The same with ONE multicast store per row segment: d_multicast_out is a multicast address that maps the same
+ * [world*clips_per_rank, frames, cols] cache on every rank (NVLink SHARP: cuMulticastCreate / cuMulticastBindMem, or
+ * torch.distributed._symmetric_memory's multicast_ptr); the epilogue issues multimem.st and the NVSwitch replicates
+ * each row to all ranks, so a row leaves the GPU once instead of world - 1 times.  Needs multicast support on the
+ * fabric (B200 HGX: yes); the caller owns the closing barrier. */
+int scf_extract_i16_gather_multicast(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
+                                     int32_t clip_len, float* d_multicast_out, int32_t world, int32_t rank,
+                                     int64_t clips_per_rank, void* cuda_stream);
+
 /* Plain NCCL all-gather of per-rank feature shards (baseline for the fused path).  nccl_comm is an
  * ncclComm_t; libnccl.so.2 is resolved with dlopen at first use. */
 int scf_allgather_nccl(void* nccl_comm, const float* d_local, int64_t n_local_floats, float* d_all,

@@ -73,12 +73,30 @@ def test_feature_cache_gather_single_process(example_pcm):
     del t
 
 
+def _dist_check(nproc, port, *extra):
+    return subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=%d' % nproc,
+                           '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'tools', 'dist_check.py'),
+                           '--clips', '4001'] + list(extra), capture_output=True, text=True, timeout=600)
+
+
 def test_two_gpus_over_ipc_when_available():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run tools/dist_check.py under gpurun --gpus 2)')
-    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
-                        '--master-addr', '127.0.0.1', '--master-port', '29517', os.path.join(ROOT, 'tools', 'dist_check.py'),
-                        '--clips', '4001'], capture_output=True, text=True, timeout=600)
+    r = _dist_check(2, 29517)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert 'DIST_CHECK_OK' in r.stdout
+
+
+def test_multicast_gather_when_available():
+    """scf_extract_i16_gather_multicast: one multimem.st per row segment to the multicast address of a torch
+    symmetric-memory cache.  Runs with every visible GPU (one process each, at most 2); a fabric or torch build without a
+    multicast mapping skips (the peer-store path above is the portable one)."""
+    import torch
+    n = min(torch.cuda.device_count(), 2)
+    r = _dist_check(n, 29518, '--multicast')
+    if r.returncode != 0 and ('no multicast address' in r.stdout + r.stderr or 'multicast' in (r.stdout + r.stderr).lower()
+                              and 'DIST_CHECK_FAILED' not in r.stdout):
+        pytest.skip('no multicast mapping on this box: ' + (r.stdout + r.stderr)[-300:].replace('\n', ' '))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert 'DIST_CHECK_OK' in r.stdout and '"multicast": true' in r.stdout

@@ -30,7 +30,7 @@ EXPORTS = [
     'scf_plan_create', 'scf_plan_destroy', 'scf_plan_config',
     'scf_extract_i16', 'scf_extract_f32', 'scf_extract_host_i16', 'scf_extract_host_f32',
     'scf_extract_host_i16_async', 'scf_host_sync',
-    'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_allgather_nccl',
+    'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_extract_i16_gather_multicast', 'scf_allgather_nccl',
     'scf_stream_create', 'scf_stream_destroy', 'scf_stream_reset', 'scf_stream_push_i16',
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
     'scf_measure_fp32_flops', 'scf_device_malloc', 'scf_device_free', 'scf_memcpy', 'scf_ipc_export',
@@ -110,6 +110,7 @@ def lib():
         L.scf_host_sync.argtypes = [vp]
         L.scf_extract_i16_dlpack.argtypes = [vp, vp, i64, i64, i32, vp, i32, ctypes.POINTER(vp), vp]
         L.scf_extract_i16_gather.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(vp), i32, i32, i64, vp]
+        L.scf_extract_i16_gather_multicast.argtypes = [vp, vp, i64, i64, i32, vp, i32, i32, i64, vp]
         L.scf_allgather_nccl.argtypes = [vp, vp, i64, vp, vp]
         L.scf_stream_create.argtypes = [vp, i32, i32, i32, ctypes.POINTER(vp)]
         L.scf_stream_destroy.argtypes = [vp]

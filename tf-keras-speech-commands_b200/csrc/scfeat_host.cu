@@ -633,7 +633,7 @@ static inline int c_hop(const scf_plan* plan) { return plan->cfg.hop; }
 static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, int64_t n_clips, int64_t clip_stride,
                           int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out,
                           float* const* peers, int world, int rank, void* cuda_stream, int64_t clips_per_rank = 0,
-                          const StreamStep* stream_step = nullptr)
+                          const StreamStep* stream_step = nullptr, bool world_is_multicast = false)
 {
     if (!plan) return fail(SCF_ERR_INVALID, "plan is NULL");
     KParams kp;
@@ -654,8 +654,10 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
         if (plan->cfg.output == SCF_OUT_POWER) return fail(SCF_ERR_INVALID, "fused gather does not support power output");
         if (plan->cfg.delta != SCF_DELTA_NONE) return fail(SCF_ERR_INVALID, "fused gather does not support delta features");
         kp.out = nullptr;
-        kp.n_peers = world;
-        for (int r = 0; r < world; ++r) {
+        const bool multicast = world_is_multicast;
+        kp.n_peers = multicast ? 1 : world;
+        kp.peer_multicast = multicast ? 1 : 0;
+        for (int r = 0; r < kp.n_peers; ++r) {
             if (!peers[r]) return fail(SCF_ERR_INVALID, "peer pointer is NULL");
             if (reinterpret_cast<uintptr_t>(peers[r]) & 15) return fail(SCF_ERR_INVALID, "peer buffers must be 16-byte aligned");
             kp.peer_out[r] = peers[r];
@@ -1151,6 +1153,16 @@ int scf_extract_i16_gather(const scf_plan* plan, const int16_t* d_pcm, int64_t n
     if (!d_peer_out) return fail(SCF_ERR_INVALID, "peer table is NULL");
     return extract_device(plan, false, d_pcm, n_local, clip_stride, clip_len, nullptr, SCF_PAD_FRONT_ZERO, nullptr,
                           d_peer_out, world, rank, cuda_stream, clips_per_rank);
+}
+
+int scf_extract_i16_gather_multicast(const scf_plan* plan, const int16_t* d_pcm, int64_t n_local, int64_t clip_stride,
+                                     int32_t clip_len, float* d_multicast_out, int32_t world, int32_t rank,
+                                     int64_t clips_per_rank, void* cuda_stream)
+{
+    if (!d_multicast_out) return fail(SCF_ERR_INVALID, "multicast pointer is NULL");
+    float* table[1] = {d_multicast_out};
+    return extract_device(plan, false, d_pcm, n_local, clip_stride, clip_len, nullptr, SCF_PAD_FRONT_ZERO, nullptr,
+                          table, world, rank, cuda_stream, clips_per_rank, nullptr, true);
 }
 
 // ---- device memory / CUDA IPC helpers ------------------------------------------------------------

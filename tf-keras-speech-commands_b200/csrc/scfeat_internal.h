@@ -83,6 +83,7 @@ struct KParams {
     float* out;                  // rank-local output, or NULL when peer_out is used
     float* peer_out[kMaxPeers];  // fused all-gather targets
     int32_t n_peers;             // 0 = plain
+    int32_t peer_multicast;      // 1: peer_out[0] is a multicast address of all ranks' caches (multimem.st, one store per row segment)
     int64_t peer_row0;           // first output row of this rank inside the gathered cache
     int32_t out_cols;            // columns the kernel produces per row
     int32_t out_pitch;           // floats between rows of `out` (> out_cols when delta columns follow)

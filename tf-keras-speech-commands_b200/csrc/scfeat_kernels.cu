@@ -811,7 +811,14 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     if (row < 0) continue;
                     const float4 v = reinterpret_cast<const float4*>(s_stage)[i];
                     const int64_t off = (p.peer_row0 + row) * c4 + (i - sl * c4);
-                    for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_out[r])[off] = v;
+                    if (p.peer_multicast) {       // one store to the multicast address: the switch replicates it
+                        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(
+                                         reinterpret_cast<float4*>(p.peer_out[0]) + off),
+                                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                                     : "memory");
+                    } else {
+                        for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_out[r])[off] = v;
+                    }
                 }
             } else {
                 for (int i = tid; i < n; i += kThreads) {
@@ -820,7 +827,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     if (row < 0) continue;
                     const float v = s_stage[i];
                     const int64_t off = (p.peer_row0 + row) * p.out_cols + (i - sl * p.out_cols);
-                    for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
+                    if (p.peer_multicast) {
+                        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.peer_out[0] + off), "f"(v) : "memory");
+                    } else {
+                        for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][off] = v;
+                    }
                 }
             }
         };

@@ -6,6 +6,10 @@ process that calls model.fit) is the full [N, frames, cols] tensor on every rank
 every rank a peer-mapped view of every rank's cache (CUDA IPC over NVLink) and the extraction kernel's epilogue
 stores each finished row into all of them (scf_extract_i16_gather) -- the all-gather is fused into the compute
 kernel.  torch.distributed is used only to exchange the 64-byte IPC handles and for the closing barrier.
+
+With ``multicast=True`` the cache is allocated as torch symmetric memory and the epilogue issues ONE ``multimem.st`` per
+row segment to the multicast address of all ranks' caches (scf_extract_i16_gather_multicast): the NVSwitch replicates
+the row, so it leaves the GPU once instead of world - 1 times.
 """
 import ctypes
 
@@ -31,7 +35,7 @@ class FeatureCacheGather:
     process emulate several ranks on one GPU (tests): a list of device pointers standing for the ranks' caches.
     """
 
-    def __init__(self, plan, n_clips, clip_len, world, rank, device, group=None):
+    def __init__(self, plan, n_clips, clip_len, world, rank, device, group=None, multicast=False):
         self.plan, self.n_clips, self.clip_len = plan, int(n_clips), int(clip_len)
         self.world, self.rank, self.device = int(world), int(rank), int(device)
         self.frames = plan.frames(clip_len)
@@ -40,9 +44,14 @@ class FeatureCacheGather:
         self.rows = self.world * self.per_rank
         self.bytes = self.rows * self.frames * self.cols * 4
         self._own = ctypes.c_void_p()
+        self._imported = []
+        self._symm = None                  # (tensor, handle) when the cache is torch symmetric memory
+        self.multicast_ptr = 0
+        if multicast:
+            self._init_multicast(group)
+            return
         check(_lib.lib().scf_device_malloc(self.device, self.bytes, ctypes.byref(self._own)))
         self._peers = [None] * self.world
-        self._imported = []
         self._peers[self.rank] = self._own.value
         if self.world > 1:
             if group is None:
@@ -62,6 +71,24 @@ class FeatureCacheGather:
                 self._imported.append(p.value)
         self._table = (ctypes.c_void_p * self.world)(*self._peers)
 
+    def _init_multicast(self, group):
+        """Cache in torch symmetric memory; needs a process group and multicast support on the fabric."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if group is None:
+            group = dist.group.WORLD
+        t = symm_mem.empty(self.bytes // 4, dtype=torch.float32, device=torch.device('cuda', self.device))
+        hdl = symm_mem.rendezvous(t, group=group)
+        mc = int(getattr(hdl, 'multicast_ptr', 0) or 0)
+        if mc == 0:
+            raise _lib.ScfError(-4, 'no multicast address for the symmetric cache (fabric without NVLink SHARP multicast?)')
+        self._symm = (t, hdl)
+        self._own = ctypes.c_void_p(t.data_ptr())
+        self.multicast_ptr = mc
+        self._peers = [int(p) for p in hdl.buffer_ptrs]
+        self._table = (ctypes.c_void_p * self.world)(*self._peers)
+
     @property
     def ptr(self):
         return self._own.value
@@ -70,6 +97,12 @@ class FeatureCacheGather:
         """Extracts this rank's `count` clips (device int16 [count, clip_stride]) and stores every row into
         all ranks' caches.  Stream-ordered; call barrier() (or torch.distributed.barrier) before reading."""
         if self.count == 0:
+            return
+        if self.multicast_ptr:
+            check(_lib.lib().scf_extract_i16_gather_multicast(self.plan.handle, d_pcm_local, self.count,
+                                                              self.clip_len if clip_stride is None else clip_stride,
+                                                              self.clip_len, self.multicast_ptr, self.world, self.rank,
+                                                              self.per_rank, stream))
             return
         check(_lib.lib().scf_extract_i16_gather(self.plan.handle, d_pcm_local, self.count,
                                                 self.clip_len if clip_stride is None else clip_stride,
@@ -95,7 +128,11 @@ class FeatureCacheGather:
         for p in self._imported:
             _lib.lib().scf_ipc_close(self.device, p)
         self._imported = []
-        if self._own:
+        if self._symm is not None:           # torch owns the symmetric allocation
+            self._symm = None
+            self._own = ctypes.c_void_p()
+            self.multicast_ptr = 0
+        elif self._own:
             _lib.lib().scf_device_free(self.device, self._own)
             self._own = ctypes.c_void_p()
 

@@ -25,6 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--clips', type=int, default=105829)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--multicast', action='store_true', help='one multimem.st per row segment to the multicast address '
+                    'of a torch symmetric-memory cache instead of world - 1 peer stores')
     args = ap.parse_args()
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -35,7 +37,7 @@ def main():
     g = torch.Generator(device='cuda')
     g.manual_seed(1000 + rank)
     d_pcm = torch.randint(-32768, 32768, (max(count, 1), 16000), dtype=torch.int16, device='cuda', generator=g)
-    cache = FeatureCacheGather(plan, n, 16000, world, rank, local, group=dist.group.WORLD)
+    cache = FeatureCacheGather(plan, n, 16000, world, rank, local, group=dist.group.WORLD, multicast=args.multicast)
     st = torch.cuda.current_stream()
     dist.barrier()
     cache.extract_and_gather(d_pcm.data_ptr(), stream=st.cuda_stream)
@@ -79,7 +81,7 @@ def main():
         dist.all_gather_into_tensor(full, mine)
     t_nccl = timed(nccl_path)
     if rank == 0:
-        print(json.dumps({'world': world, 'clips': n, 'per_rank': per, 'ok': bool(int(flag)),
+        print(json.dumps({'world': world, 'clips': n, 'per_rank': per, 'ok': bool(int(flag)), 'multicast': bool(args.multicast),
                           'extract_only_ms': t_extract, 'fused_extract_gather_ms': t_fused, 'extract_plus_nccl_allgather_ms': t_nccl,
                           'fused_clips_per_s': n / (t_fused * 1e-3), 'extract_only_clips_per_s': n / (t_extract * 1e-3)}))
         print('DIST_CHECK_OK' if int(flag) else 'DIST_CHECK_FAILED')
