@@ -143,10 +143,13 @@ __device__ __forceinline__ ClipGeom clip_geom(const KParams& p, int64_t clip)
 // the new chunk).  Every lane issues all its loads of BOTH frames back to back as predicated loads off two base
 // pointers with immediate offsets (no per-sample address arithmetic; out-of-range positions read nothing and are
 // zero), so the memory latency is paid once per pair, not once per sample.
-template <int R, typename InT, bool STREAM>
+// `mid` runs after the loads of both frames have been issued and before their values are used: work placed there
+// (the state carry-over of a streaming step) overlaps the memory latency of the samples.
+template <int R, typename InT, bool STREAM, typename Mid>
 __device__ __forceinline__ void load_pair_generic(const KParams& p, const InT* __restrict__ clip_base,
                                                   const InT* __restrict__ tail, int split, const ClipGeom& cg, int frame_a,
-                                                  int lane, float (&xa)[R], float (&xb)[R], uint32_t& nz_a, uint32_t& nz_b)
+                                                  int lane, float (&xa)[R], float (&xb)[R], uint32_t& nz_a, uint32_t& nz_b,
+                                                  Mid&& mid)
 {
     typedef typename Raw<InT>::type RawT;
     // frame f covers clip samples s0 + n, n < w_eff; n is valid for lo <= n < lo + width
@@ -180,6 +183,7 @@ __device__ __forceinline__ void load_pair_generic(const KParams& p, const InT* _
     RawT ra[R], rb[R];
     fetch(sa, 0, ra);
     fetch(sb, 0, rb);
+    mid();
 #pragma unroll
     for (int i = 0; i < R; ++i) { xa[i] = to_f32(ra[i]); xb[i] = to_f32(rb[i]); }
     if (p.preemph != 0.f) {                                   // x[a] - alpha * x[a-1], x[-1] := 0 (mfcc.h:394-403)
@@ -434,6 +438,94 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 dst[j] = ld_sample_if(cb + (e0 - pad + lane + 32 * j - 1), j >= j0 && j < n_ld);
         }
     };
+    // Streaming step: state carry-over of stream `clip` (listen.py:106-109), split over the warps that own its pairs:
+    // the warp of pair 0 writes the new carry concat(carry, chunk)[k * hop:] and the step's counters, the warp of pair 1
+    // (pair 0 when a step has a single pair) moves the surviving ring rows up by k -- the k new rows are written by
+    // whoever computes them.  Everything is read from the `in` buffers and written to the `out` buffers, so the order
+    // among warps, teams and launches' threads does not matter.  Called between the issue and the first use of the
+    // pair's sample loads, with its own loads in flight 16 (carry) or 8 x 16 bytes (ring) at a time: one or two memory round trips, hidden behind the
+    // samples' (the first version ran after the DCT in rounds of 8 loads per lane: 12.7 -> see DESIGN.md 4.2).
+    auto stream_move = [&](uint32_t clip, uint32_t q) {
+        if constexpr (!FAST && sizeof(InT) == 2) {
+            const StreamStep& ss = p.stream;
+            const bool do_carry = q == 0, do_ring = q == (ppc > 1 ? 1u : 0u);
+            if (!do_carry && !do_ring) return;
+            const int len_old = __ldg(ss.len_in + clip);
+            const int len = len_old + ss.chunk_len;
+            const int k = (len >= p.window) ? (len - p.window) / p.hop + 1 : 0;
+            const int consumed = k * p.hop, keep = len - consumed;
+            if (do_carry) {
+                const int16_t* cin = ss.carry_in + (int64_t)clip * ss.carry_cap;
+                const int16_t* ch = ss.chunks + (int64_t)clip * ss.chunk_len;
+                int16_t* cout = ss.carry_out + (int64_t)clip * ss.carry_cap;
+                for (int j0 = lane; j0 < keep; j0 += 32 * 16) {              // keep < window + hop: two rounds as a rule
+                    int16_t v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int j = j0 + 32 * u, a = consumed + j;
+                        v[u] = j < keep ? (a < len_old ? __ldg(cin + a) : __ldg(ch + (a - len_old))) : (int16_t)0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (j0 + 32 * u < keep) cout[j0 + 32 * u] = v[u];
+                }
+                if (lane == 0) {
+                    ss.len_out[clip] = keep;
+                    ss.n_new[clip] = k;
+                    if (ss.n_new_copy != nullptr) ss.n_new_copy[clip] = k;
+                }
+            }
+            if (do_ring) {
+                const int cols = p.out_cols;
+                const int kk = min(k, ss.ring_rows);
+                const int n_old = (ss.ring_rows - kk) * cols;
+                const int64_t r0 = (int64_t)clip * ss.ring_rows * cols;
+                const float* src = ss.ring_in + r0 + kk * cols;
+                float* dst = ss.ring_out + r0;
+                float* cpy = ss.ring_copy != nullptr ? ss.ring_copy + (int64_t)clip * ss.ring_rows * ss.copy_pitch : nullptr;
+                const bool vec = ((cols | ss.copy_pitch) & 3) == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(ss.ring_in) | reinterpret_cast<uintptr_t>(ss.ring_out) |
+                                   reinterpret_cast<uintptr_t>(ss.ring_copy)) & 15) == 0;
+                if (vec) {                                                    // rows are multiples of 16 bytes
+                    const int n4 = n_old >> 2, c4 = cols >> 2;
+                    for (int j0 = lane; j0 < n4; j0 += 32 * 8) {
+                        float4 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = j0 + 32 * u < n4 ? __ldg(reinterpret_cast<const float4*>(src) + j0 + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + 32 * u;
+                            if (j < n4) {
+                                reinterpret_cast<float4*>(dst)[j] = v[u];
+                                if (cpy != nullptr) {
+                                    const int rr = j / c4;
+                                    reinterpret_cast<float4*>(cpy + (int64_t)rr * ss.copy_pitch)[j - rr * c4] = v[u];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int j0 = lane; j0 < n_old; j0 += 32 * 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = j0 + 32 * u < n_old ? __ldg(src + j0 + 32 * u) : 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = j0 + 32 * u;
+                            if (j < n_old) {
+                                dst[j] = v[u];
+                                if (cpy != nullptr) {
+                                    const int rr = j / cols;
+                                    cpy[(int64_t)rr * ss.copy_pitch + (j - rr * cols)] = v[u];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    };
     // classic variant: the samples of the NEXT tile are fetched into registers while the bank / log / DCT phases of
     // the current tile run (those need few registers), so the FFT stage never waits on HBM
     // (float input keeps 48 full registers busy that way and spills: it loads at the point of use instead;
@@ -548,10 +640,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                             if constexpr (sizeof(InT) == 2) {
                                 const int split = cg.len - p.stream.chunk_len;          // carry, then the new chunk
                                 const InT* tail = reinterpret_cast<const InT*>(p.stream.chunks) + (int64_t)clip * p.stream.chunk_len;
-                                load_pair_generic<R, InT, true>(p, cb, tail, split, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
+                                load_pair_generic<R, InT, true>(p, cb, tail, split, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b,
+                                                                [&]() { stream_move(clip, q); });
                             }
                         } else {
-                            load_pair_generic<R, InT, false>(p, cb, cb, 0, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b);
+                            load_pair_generic<R, InT, false>(p, cb, cb, 0, cg, 2 * (int)q, lane, xr, xi, nz_a, nz_b, []() {});
                         }
 #pragma unroll
                         for (int i = 0; i < R; ++i) x[i] = pk(xr[i], xi[i]);
@@ -835,69 +928,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 }
             }
         };
-        // Streaming step: the team that holds a stream's first pair carries its state over -- the surviving ring rows
-        // move up by k (the k new rows were just written by whoever computed them), the carry becomes
-        // concat(carry, chunk)[k * hop:] (listen.py:106-109).  Everything is read from the `in` buffers and written to
-        // the `out` buffers, so the order among teams and launches' threads does not matter.
-        auto stream_update = [&]() {
-            if constexpr (!FAST && sizeof(InT) == 2) {
-                if (!p.stream_on) return;
-                const StreamStep& ss = p.stream;
-                const int cols = p.out_cols;
-                for (int i = warp; i < geo::PPT; i += kWarps) {          // one warp per stream, 8 loads in flight per lane
-                    const uint32_t gp = pair0 + i;
-                    if (gp >= n_pairs) break;
-                    uint32_t clip, q;
-                    pair_pos(gp, clip, q);
-                    if (q != 0) continue;
-                    const int len_old = __ldg(ss.len_in + clip);
-                    const int len = len_old + ss.chunk_len;
-                    const int k = (len >= p.window) ? (len - p.window) / p.hop + 1 : 0;
-                    const int consumed = k * p.hop, keep = len - consumed;
-                    const int16_t* cin = ss.carry_in + (int64_t)clip * ss.carry_cap;
-                    const int16_t* ch = ss.chunks + (int64_t)clip * ss.chunk_len;
-                    int16_t* cout = ss.carry_out + (int64_t)clip * ss.carry_cap;
-                    for (int j0 = lane; j0 < keep; j0 += 32 * 8) {
-                        int16_t v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + 32 * u, a = consumed + j;
-                            v[u] = j < keep ? (a < len_old ? __ldg(cin + a) : __ldg(ch + (a - len_old))) : (int16_t)0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (j0 + 32 * u < keep) cout[j0 + 32 * u] = v[u];
-                    }
-                    const int kk = min(k, ss.ring_rows);
-                    const int n_old = (ss.ring_rows - kk) * cols;
-                    const int64_t r0 = (int64_t)clip * ss.ring_rows * cols;
-                    for (int j0 = lane; j0 < n_old; j0 += 32 * 8) {
-                        float v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = j0 + 32 * u < n_old ? __ldg(ss.ring_in + r0 + kk * cols + j0 + 32 * u) : 0.f;
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int j = j0 + 32 * u;
-                            if (j < n_old) {
-                                ss.ring_out[r0 + j] = v[u];
-                                if (ss.ring_copy != nullptr) {
-                                    const int rr = j / cols;
-                                    ss.ring_copy[((int64_t)clip * ss.ring_rows + rr) * ss.copy_pitch + (j - rr * cols)] = v[u];
-                                }
-                            }
-                        }
-                    }
-                    if (lane == 0) {
-                        ss.len_out[clip] = keep;
-                        ss.n_new[clip] = k;
-                        if (ss.n_new_copy != nullptr) ss.n_new_copy[clip] = k;
-                    }
-                }
-            }
-        };
         if (p.out_kind == SCF_OUT_LOG_BANK) {
             if (p.n_peers != 0) push_to_peers();
-            stream_update();
             team_sync();          // the partial-sum rows live in the exchange area: the next tile's pass 1 rewrites them
             continue;
         }
@@ -939,7 +971,6 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             }
         }
         if (p.n_peers != 0) push_to_peers();
-        stream_update();
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
         // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
     }
