@@ -545,6 +545,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     };
     if (tile_first < n_tiles) prefetch(gp0, clip0, q0);
     __syncthreads();          // mbarrier init + zeroed s_logq pad rows visible (the only CTA-wide barrier)
+#ifdef SCF_STAGGER_NS        // experiment: teams of a CTA start a third of a tile apart instead of in phase
+    if constexpr (TEAMS > 1) {
+        for (int t = 0; t < team; ++t) __nanosleep(SCF_STAGGER_NS);
+    }
+#endif
 #ifdef SCF_ABL_TEAMS         // scaling experiment (profiles/r02_regular_bank_tma_staging.log): only the first n teams of a CTA work
     if (team >= SCF_ABL_TEAMS) return;
 #endif
