@@ -144,8 +144,9 @@ int scf_extract_i16(const scf_plan* plan, const int16_t* d_pcm, int64_t n_clips,
 int scf_extract_f32(const scf_plan* plan, const float* d_audio, int64_t n_clips, int64_t clip_stride,
                     int32_t clip_len, const int32_t* d_lengths, int32_t pad, float* d_out, void* cuda_stream);
 
-/* Host-buffer convenience wrappers (pinned staging, H2D, kernel, D2H, synchronous): what the
- * numpy-in / numpy-out drop-in functions call.  h_lengths may be NULL. */
+/* Host-buffer convenience wrappers (staging, H2D, kernel, D2H, synchronous): what the numpy-in / numpy-out drop-in
+ * functions call.  h_lengths may be NULL.  A call whose input + output fit into 96 KB (one clip, as the reference calls
+ * its feature functions) goes through pinned device-mapped memory instead of copies: one launch, one synchronisation. */
 int scf_extract_host_i16(const scf_plan* plan, const int16_t* h_pcm, int64_t n_clips, int64_t clip_stride,
                          int32_t clip_len, const int32_t* h_lengths, int32_t pad, float* h_out);
 int scf_extract_host_f32(const scf_plan* plan, const float* h_audio, int64_t n_clips, int64_t clip_stride,

@@ -160,8 +160,38 @@ static void build_dct(int n_filt, int n_out, std::vector<double>& d)
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
+// Pinned, device-mapped host staging for SMALL host-buffer calls (one clip, one chunk per stream -- the reference's own
+// call shape): the kernel reads its samples from this buffer over PCIe and writes its rows into it, so such a call is one
+// launch and one stream synchronisation instead of copy + launch + copy (33.8 -> see DESIGN.md section 6).
+struct MappedStage {
+    unsigned char* h = nullptr;     // host view
+    unsigned char* d = nullptr;     // device view of the same bytes
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        release();
+        if (cudaHostAlloc((void**)&h, need, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) {
+            cudaGetLastError();
+            release();
+            return -1;
+        }
+        bytes = need;
+        return 0;
+    }
+    void release()
+    {
+        if (h) cudaFreeHost(h);
+        h = d = nullptr;
+        bytes = 0;
+    }
+};
+constexpr size_t kSmallCallBytes = 96 * 1024;      // input + output of a call that takes the mapped path
+
 struct Workspace {          // scratch for the host-buffer entry points
     std::mutex mu;
+    MappedStage small;
     void* d_in = nullptr;
     size_t in_bytes = 0;
     float* d_out = nullptr;
@@ -216,6 +246,7 @@ struct scf_stream {
     int32_t n_streams = 0, carry_cap = 0, ring_rows = 0, cols = 0;
     int max_chunk = 0;
     int16_t* d_chunk_stage = nullptr;     // for the host-buffer push
+    scf::MappedStage small;               // ... of few streams (chunk in, ring + counters out through mapped memory)
 };
 
 namespace scf {
@@ -437,6 +468,7 @@ static void free_plan_tables(scf_plan* p)
     if (p->ws.st) cudaStreamDestroy(p->ws.st);
     if (p->ws.st2) cudaStreamDestroy(p->ws.st2);
     if (p->ws.ev) cudaEventDestroy(p->ws.ev);
+    p->ws.small.release();
     for (auto& sl : p->ws.slot) {
         if (sl.d_in) cudaFree(sl.d_in);
         if (sl.d_out) cudaFree(sl.d_out);
@@ -738,6 +770,25 @@ static int extract_host(const scf_plan* plan, bool is_f32, const void* h_in, int
     const size_t row_bytes = (size_t)fpc * plan->out_cols * sizeof(float);
     const size_t out_bytes = (size_t)n_clips * row_bytes;
     int rc;
+    // small call: the kernel reads the samples from / writes the rows to mapped host memory -- one launch, one sync
+    const size_t len_bytes = h_lengths ? (((size_t)n_clips * 4 + 15) & ~(size_t)15) : 0;
+    const size_t in_al = (in_bytes + 15) & ~(size_t)15;
+    if (in_al + len_bytes + out_bytes <= kSmallCallBytes && ws.small.ensure(kSmallCallBytes) == 0) {
+        unsigned char* hs = ws.small.h;
+        unsigned char* ds = ws.small.d;
+        memcpy(hs, h_in, in_bytes);
+        if (h_lengths) memcpy(hs + in_al, h_lengths, (size_t)n_clips * 4);
+        float* h_rows = reinterpret_cast<float*>(hs + in_al + len_bytes);
+        if (pad == SCF_PAD_NONE && h_lengths) memset(h_rows, 0, out_bytes);     // rows of short clips stay untouched
+        rc = extract_device(plan, is_f32, ds, n_clips, clip_stride, clip_len,
+                            h_lengths ? reinterpret_cast<const int32_t*>(ds + in_al) : nullptr, pad,
+                            reinterpret_cast<float*>(ds + in_al + len_bytes), nullptr, 0, 0, ws.st);
+        cudaError_t se = cudaStreamSynchronize(ws.st);
+        if (rc) return rc;
+        if (se != cudaSuccess) return fail(SCF_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(se));
+        memcpy(h_out, h_rows, out_bytes);
+        return SCF_OK;
+    }
     if ((rc = grow(&ws.d_in, &ws.in_bytes, in_bytes)) || (rc = grow(&ws.d_out, &ws.out_bytes, out_bytes))) return rc;
     const int32_t* d_len = nullptr;
     if (h_lengths) {
@@ -1297,6 +1348,7 @@ void scf_stream_destroy(scf_stream* s)
     cudaFree(s->ring_wide);
     cudaFree(s->n_new);
     cudaFree(s->d_chunk_stage);
+    s->small.release();
     delete s;
 }
 
@@ -1349,6 +1401,24 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
     if (!s || !h_chunks) return fail(SCF_ERR_INVALID, "NULL argument");
     if (chunk_len < 1 || chunk_len > s->max_chunk) return fail(SCF_ERR_INVALID, "chunk_len outside 1..max_chunk");
     DeviceGuard guard(s->plan->device);
+    {   // few streams (the single-microphone Listener): chunk in, ring + counters out through mapped host memory
+        const size_t cb = (((size_t)s->n_streams * chunk_len * 2) + 15) & ~(size_t)15;
+        const size_t rb = (size_t)s->n_streams * s->ring_rows * s->plan->out_cols * 4;
+        const size_t nb = (size_t)s->n_streams * 4;
+        if (cb + rb + nb <= kSmallCallBytes && s->small.ensure(kSmallCallBytes) == 0) {
+            memcpy(s->small.h, h_chunks, (size_t)s->n_streams * chunk_len * 2);
+            float* d_ring = h_ring_out ? reinterpret_cast<float*>(s->small.d + cb) : nullptr;
+            int32_t* d_new = h_new_rows ? reinterpret_cast<int32_t*>(s->small.d + cb + rb) : nullptr;
+            // (the default stream, like the copying path below: ordered behind whatever this stream object did before)
+            int rc = scf_stream_push_i16(s, reinterpret_cast<const int16_t*>(s->small.d), chunk_len, d_ring, d_new, nullptr);
+            cudaError_t se = cudaStreamSynchronize(nullptr);
+            if (rc) return rc;
+            if (se != cudaSuccess) return fail(SCF_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(se));
+            if (h_ring_out) memcpy(h_ring_out, s->small.h + cb, rb);
+            if (h_new_rows) memcpy(h_new_rows, s->small.h + cb + rb, nb);
+            return SCF_OK;
+        }
+    }
     SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)s->n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
     // delta plans hand out wide rows: the step writes them (and their delta columns) into the stream's wide copy
     float* wide = (h_ring_out && s->ring_wide) ? s->ring_wide : nullptr;
