@@ -82,7 +82,7 @@ def _run(audio, out_kind, sample_rate, window_size, hop_size, fft_size, **kw):
         a = a.astype(np.float32, copy=False)
     plan = get_plan(sample_rate=int(sample_rate), window=int(window_size), hop=int(hop_size), n_fft=int(fft_size),
                     bank=BANK_BARK_REF, output=out_kind, **kw)
-    if _lib.num_frames(len(a), int(window_size), int(hop_size)) == 0:
+    if plan.frames(len(a)) == 0:
         return np.empty((0, plan.out_cols), dtype=np.float32)
     return plan.extract_host(a, pad=PAD_NONE)
 

@@ -64,7 +64,7 @@ struct Geo {
 template <int PPT>
 __host__ __device__ inline int team_smem_floats(const KParams& p)
 {
-    const int n_lq = p.n_q > p.n_filt4 ? p.n_q : p.n_filt4;
+    const int n_lq = ((p.n_q > p.n_filt4 ? p.n_q : p.n_filt4) + 1) & ~1;
     return 2 * PPT * (n_lq + 2) + (p.n_peers != 0 ? 2 * PPT * (p.out_cols + 2) : 0);
 }
 
@@ -298,8 +298,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     const uint32_t* s_tasks = reinterpret_cast<const uint32_t*>(s_tab + p.off_tasks);
     const int32_t* s_tbeg = reinterpret_cast<const int32_t*>(s_tab + p.off_tbeg);
     const int2* s_qspec = reinterpret_cast<const int2*>(s_tab + p.off_qspec);
-    const int n_lq = max(p.n_q, p.n_filt4);          // DCT reads n_filt4 rows; the pad rows stay zero
-    // per team: log bands [n_lq][slot] as packed (A, B) pairs, per-slot info (frame energies + output row); with the
+    // DCT reads n_filt4 rows; the pad rows stay zero.  Rows are stored in pairs, [q / 2][slot][q & 1], so that the DCT
+    // fetches two bands of its slot per 128-bit load (one wavefront per quarter-warp row pair; + 0.5 % on the 512-clip batch)
+    const int n_lq = (max(p.n_q, p.n_filt4) + 1) & ~1;
+    auto lq = [&](int q, int sl) { return ((q >> 1) * geo::PPT + sl) * 2 + (q & 1); };
+    // per team: log bands [n_lq / 2][slot][2] as packed (A, B) pairs, per-slot info (frame energies + output row); with the
     // fused all-gather also the finished rows [frame slot][col] and their row ids (int64)
     const int team_floats = team_smem_floats<geo::PPT>(p);
     f2* s_logq = reinterpret_cast<f2*>(reinterpret_cast<float*>(s_tab + staged_bytes) + team * team_floats);
@@ -887,7 +890,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                     }
                 }
             } else {
-                s_logq[q * geo::PPT + slot] = pk(la, lb);
+                s_logq[lq(q, slot)] = pk(la, lb);
             }
         }
         // Fused all-gather: the finished rows of this tile sit contiguously in shared memory [frame slot][col]; every
@@ -949,8 +952,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             f2 a0 = pk(0.f, 0.f), a1 = pk(0.f, 0.f);
             for (int m = 0; m < p.n_filt4; m += 4) {
                 // rows >= n_filt carry zero DCT weights (energy row is finite, pad rows are zero)
-                const f2 l0 = s_logq[(m + 0) * geo::PPT + slot], l1 = s_logq[(m + 1) * geo::PPT + slot];
-                const f2 l2 = s_logq[(m + 2) * geo::PPT + slot], l3 = s_logq[(m + 3) * geo::PPT + slot];
+                const ulonglong2 l01 = *reinterpret_cast<const ulonglong2*>(s_logq + lq(m, slot));
+                const ulonglong2 l23 = *reinterpret_cast<const ulonglong2*>(s_logq + lq(m + 2, slot));
+                const f2 l0 = l01.x, l1 = l01.y, l2 = l23.x, l3 = l23.y;
                 const float4 d = kTwInL1 ? __ldg(d4 + (m >> 2)) : d4[m >> 2];
                 a0 = fma2(l0, bc(d.x), a0);
                 a1 = fma2(l1, bc(d.y), a1);
@@ -958,7 +962,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 a1 = fma2(l3, bc(d.w), a1);
             }
             f2 v = add2(a0, a1);
-            if (c == 0) v = s_logq[p.n_filt * geo::PPT + slot];
+            if (c == 0) v = s_logq[lq(p.n_filt, slot)];
             if (p.n_peers != 0) {
                 s_stage[(2 * slot) * p.out_cols + c] = lo(v);
                 s_stage[(2 * slot + 1) * p.out_cols + c] = hi(v);

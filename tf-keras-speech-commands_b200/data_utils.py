@@ -63,7 +63,7 @@ def vectorize_raw(audio):
     if a.dtype != np.int16:
         a = a.astype(np.float32, copy=False)
     plan = _mfcc_plan()
-    if _lib.num_frames(len(a), plan.window, plan.hop) == 0:
+    if plan.frames(len(a)) == 0:
         return np.empty((0, plan.out_cols), dtype=np.float32)
     return plan.extract_host(a, pad=PAD_NONE)
 

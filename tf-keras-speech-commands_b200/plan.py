@@ -40,7 +40,9 @@ class Plan:
         return self._h
 
     def frames(self, n_samples):
-        return _lib.num_frames(n_samples, self.window, self.hop)
+        """scf_num_frames (chop_array's frame count) without the ctypes round trip."""
+        n = int(n_samples)
+        return 0 if n < self.window else (n - self.window) // self.hop + 1
 
     # ---- host numpy in -> host numpy out (what the drop-in functions use) ----------------------
     def extract_host(self, clips, lengths=None, pad=PAD_FRONT_ZERO, out=None):

@@ -42,7 +42,7 @@ def _run(audio, out_kind, window_stride, fft_size, **kw):
     a = _as_input(audio)
     window, hop = int(window_stride[0]), int(window_stride[1])
     plan = get_plan(window=window, hop=hop, n_fft=int(fft_size), output=out_kind, **kw)
-    if _lib.num_frames(len(a), window, hop) == 0:
+    if plan.frames(len(a)) == 0:
         return np.empty((0, plan.out_cols), dtype=np.float32)
     return plan.extract_host(a, pad=PAD_NONE)
 
