@@ -53,3 +53,16 @@ try:
     bench('CPU oracle: Listener.update_vectors emulation', lambda: lo.update_vectors(chunk), n=300)
 except Exception as e:
     print('oracle not available:', e)
+
+# ---- batches from ordinary (pageable) numpy arrays: extract_features_batch, the cache builder's call ----------------
+for n in (8, 64, 512, 4096):
+    batch = rng.integers(-32768, 32768, size=(n, 16000), dtype=np.int16)
+    fn = lambda: scfeat.data_utils.extract_features_batch(batch)
+    for _ in range(5):
+        fn()
+    reps = max(5, min(200, 20000 // n))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    dt = (time.perf_counter() - t0) / reps
+    print('extract_features_batch(%4d pageable int16 clips)              %8.1f us per call = %7.1f k clips/s' % (n, dt * 1e6, n / dt / 1e3))
