@@ -308,6 +308,11 @@ int scf_ipc_import(int32_t device, const uint8_t* handle64, void** d_ptr_out);
 int scf_ipc_close(int32_t device, void* d_ptr);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
+/* dst[0 .. bytes) = src[0 .. bytes) with the library's persistent copy threads (what the host-buffer calls use to move
+ * pageable caller arrays into pinned staging; SCFEAT_COPY_THREADS, default half the allowed cores, at most 8).  Host
+ * only, no GPU involved; safe to call from several threads. */
+int scf_parallel_memcpy(void* dst, const void* src, int64_t bytes);
+
 const char* scf_last_error(void);
 int scf_version(void);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches claim). */

@@ -259,3 +259,31 @@ def test_add_deltas_both_definitions(ref_cpp):
     np.testing.assert_array_equal(d[1:, 20:], base[1:] - base[:-1])
     with pytest.raises(ValueError):
         scfeat.data_utils.add_deltas(base, kind='other')
+
+
+def test_parallel_memcpy_sizes_and_concurrent_callers():
+    """The copy threads of the pageable staging path (scf_parallel_memcpy): every size class (one part, uneven parts,
+    tails that are not multiples of the 64-byte split) and four callers at once."""
+    import threading
+    L = _lib.lib()
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 63, 4096, 256 * 1024 - 1, 256 * 1024, 1_000_003, 5 * 1024 * 1024 + 17):
+        src = rng.integers(0, 256, size=n, dtype=np.uint8)
+        dst = np.zeros(n + 64, dtype=np.uint8)
+        _lib.check(L.scf_parallel_memcpy(dst.ctypes.data, src.ctypes.data, n))
+        assert np.array_equal(dst[:n], src) and not dst[n:].any()
+    assert L.scf_parallel_memcpy(None, None, 8) != 0           # NULL with a size is an error, not a crash
+    srcs = [rng.integers(0, 256, size=3_000_000 + 1000 * i, dtype=np.uint8) for i in range(4)]
+    dsts = [np.zeros_like(s) for s in srcs]
+    errs = []
+
+    def work(i):
+        for _ in range(5):
+            dsts[i][:] = 0
+            if L.scf_parallel_memcpy(dsts[i].ctypes.data, srcs[i].ctypes.data, srcs[i].size) != 0 or \
+                    not np.array_equal(dsts[i], srcs[i]):
+                errs.append(i)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs

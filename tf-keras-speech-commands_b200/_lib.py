@@ -33,7 +33,7 @@ EXPORTS = [
     'scf_extract_i16_dlpack', 'scf_dlpack_make_capsule', 'scf_extract_i16_gather', 'scf_extract_i16_gather_multicast', 'scf_allgather_nccl',
     'scf_stream_create', 'scf_stream_destroy', 'scf_stream_reset', 'scf_stream_push_i16',
     'scf_stream_push_host_i16', 'scf_last_error', 'scf_version', 'scf_launch_count',
-    'scf_measure_fp32_flops', 'scf_device_malloc', 'scf_device_free', 'scf_memcpy', 'scf_ipc_export',
+    'scf_measure_fp32_flops', 'scf_parallel_memcpy', 'scf_device_malloc', 'scf_device_free', 'scf_memcpy', 'scf_ipc_export',
     'scf_ipc_import', 'scf_ipc_close',
     'scf_post_build_cd', 'scf_post_create', 'scf_post_destroy', 'scf_post_reset', 'scf_post_decode', 'scf_post_step',
     'scf_post_trigger_update', 'scf_post_state', 'scf_post_info',
@@ -122,6 +122,7 @@ def lib():
         L.scf_version.restype = i32
         L.scf_launch_count.restype = i64
         L.scf_measure_fp32_flops.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
+        L.scf_parallel_memcpy.argtypes = [vp, vp, i64]
         L.scf_device_malloc.argtypes = [i32, i64, ctypes.POINTER(vp)]
         L.scf_device_free.argtypes = [i32, vp]
         L.scf_memcpy.argtypes = [i32, vp, vp, i64, i32, vp]

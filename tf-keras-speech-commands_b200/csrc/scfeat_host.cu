@@ -1602,6 +1602,13 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
 }
 
 // ---- misc -------------------------------------------------------------------------------------
+int scf_parallel_memcpy(void* dst, const void* src, int64_t bytes)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(SCF_ERR_INVALID, "bad argument");
+    if (bytes > 0) CopyPool::get().copy(dst, src, (size_t)bytes);
+    return SCF_OK;
+}
+
 const char* scf_last_error(void) { return g_err.c_str(); }
 int scf_version(void) { return SCF_VERSION; }
 int64_t scf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
