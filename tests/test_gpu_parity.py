@@ -657,6 +657,42 @@ def test_ragged_batch_fast_path_random_lengths(example_pcm):
     assert_cepstrum_close(d_out.cpu().numpy(), want)
 
 
+def test_dynamic_tile_schedule_equals_round_robin(example_pcm):
+    """Launches with more than three tiles per team draw their tiles from a global counter (the team that finishes
+    early takes more): the rows must equal, bit for bit, what small launches (fixed round robin) give for the same clips
+    -- for the cepstrum and the log-bank output, three times in a row (every launch takes a fresh counter word and
+    leaves it zeroed), and for a ragged batch."""
+    import torch
+    _, pcm = example_pcm
+    n = 6000                                            # 11,250 tiles on 444 teams
+    rng = np.random.default_rng(11)
+    shifts = rng.integers(0, 16000, size=n)
+    clips = np.stack([np.roll(pcm[i % 8], shifts[i]) for i in range(n)])
+    d_in = torch.from_numpy(clips).cuda()
+    lengths = rng.integers(0, 16001, size=n).astype(np.int32)
+    d_len = torch.from_numpy(lengths).cuda()
+    for kw in (dict(), dict(output=scfeat.plan.OUT_LOG_BANK)):
+        plan = scfeat.get_plan(**kw)
+        small = torch.empty((n, 30, 20), dtype=torch.float32, device='cuda')
+        for a in range(0, n, 500):                      # 938 tiles per launch: round robin
+            plan.extract_device(d_in[a].data_ptr(), min(500, n - a), 16000, small[a].data_ptr())
+        torch.cuda.synchronize()
+        for rep in range(3):
+            big = torch.zeros((n, 30, 20), dtype=torch.float32, device='cuda')
+            plan.extract_device(d_in.data_ptr(), n, 16000, big.data_ptr())
+            torch.cuda.synchronize()
+            assert torch.equal(big, small), (kw, rep)
+        small_r = torch.empty((n, 30, 20), dtype=torch.float32, device='cuda')
+        for a in range(0, n, 500):
+            plan.extract_device(d_in[a].data_ptr(), min(500, n - a), 16000, small_r[a].data_ptr(), d_lengths=d_len[a:].data_ptr())
+        big_r = torch.zeros((n, 30, 20), dtype=torch.float32, device='cuda')
+        plan.extract_device(d_in.data_ptr(), n, 16000, big_r.data_ptr(), d_lengths=d_len.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(big_r, small_r), kw
+    want = np.stack([osonopy.mfcc_spec(a, 16000, (1024, 512), 1024, 20, 20) for a in audio_of(clips[::997])])
+    assert_cepstrum_close(scfeat.get_plan().extract_host(clips)[::997], want)
+
+
 def test_one_plan_shared_by_threads_and_streams(example_pcm):
     """include/scfeat.h: plans are immutable and may be shared between threads.  Four threads drive the same plan on
     their own CUDA streams (device API) and through the host-buffer API at once; every result must equal the

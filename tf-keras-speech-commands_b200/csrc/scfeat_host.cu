@@ -328,8 +328,13 @@ struct scf_plan {
     unsigned char* d_tab_f32 = nullptr;   // ... by the float-input power scale
     int table_bytes = 0, table_small_bytes = 0, off_wts = 0, off_tw = 0, off_dct = 0, off_tasks = 0, off_tbeg = 0, off_qspec = 0;
     int n_tasks = 0, n_q = 0, n_dst = 0, n_filt4 = 0, n_out = 0;
+    // tile counters of the dynamic schedule: a ring of zeroed words; every fast-path launch takes the next one and the
+    // team that draws the launch's last number zeroes it again (a word comes round again 16384 launches later)
+    uint32_t* d_tile_ctr = nullptr;
+    mutable std::atomic<uint32_t> ctr_next{0};
     scf::Workspace ws;
 };
+constexpr uint32_t kTileCtrRing = 16384;
 
 struct scf_stream {
     const scf_plan* plan = nullptr;
@@ -558,7 +563,7 @@ static void magic_div(uint32_t d, uint32_t& magic, uint32_t& shift)
 
 static void free_plan_tables(scf_plan* p)
 {
-    cudaFree(p->d_win); cudaFree(p->d_tab_i16); cudaFree(p->d_tab_f32);
+    cudaFree(p->d_win); cudaFree(p->d_tab_i16); cudaFree(p->d_tab_f32); cudaFree(p->d_tile_ctr);
     if (p->ws.d_in) cudaFree(p->ws.d_in);
     if (p->ws.d_out) cudaFree(p->ws.d_out);
     if (p->ws.d_len) cudaFree(p->ws.d_len);
@@ -629,6 +634,15 @@ static int plan_create(const scf_config* cfg, scf_plan** out)
         }
         rc = upload(&p->d_win, win);
         if (rc) { free_plan_tables(p); delete p; return rc; }
+    }
+    {
+        cudaError_t e = cudaMalloc((void**)&p->d_tile_ctr, (size_t)kTileCtrRing * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(p->d_tile_ctr, 0, (size_t)kTileCtrRing * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            free_plan_tables(p);
+            delete p;
+            return fail(SCF_ERR_ALLOC, std::string("tile counters: ") + cudaGetErrorString(e));
+        }
     }
     // ---- the table blob -------------------------------------------------------------------------------
     TaskList tl;
@@ -820,6 +834,11 @@ static int extract_device(const scf_plan* plan, bool is_f32, const void* d_in, i
         k.peer_row0 = kp.peer_row0 + row0;
         k.n_pairs = nc * (int64_t)kp.pairs_per_clip;
         const int64_t tiles = (k.n_pairs + ppt - 1) / ppt;
+        // (a team's first three tiles are fixed: smaller launches -- the 512-clip batch has 2.2 tiles per team -- keep the
+        //  round robin and skip the draws)
+        if (fast && !stream_step && plan->d_tile_ctr != nullptr && plan->cfg.output != SCF_OUT_POWER &&
+            tiles > 3 * 3 * (int64_t)plan->num_sms)
+            k.tile_ctr = plan->d_tile_ctr + plan->ctr_next.fetch_add(1, std::memory_order_relaxed) % kTileCtrRing;
         SCF_CUDA(launch_extract(plan->radix_r, is_f32, fast, k, tiles, plan->num_sms, (cudaStream_t)cuda_stream, smem));
     }
     // delta columns: a second, tiny pass over the finished rows (it needs the neighbouring frames of every row, which

@@ -105,6 +105,7 @@ struct KParams {
     uint32_t ppc_magic, ppc_shift;   // fast division by pairs_per_clip
     int32_t fast_path;           // 1: window == n_fft, hop == n_fft/2, full or front-padded clips (FAST kernels)
     int32_t fast_pre;            // ... with pre-emphasis and / or a window table fused into the loader (`win` is never NULL then)
+    uint32_t* tile_ctr;          // nullable: next-tile counter of this launch, zero at launch (and again when it ends)
     int32_t stream_on;           // 1: `stream` describes a streaming step (in == stream.carry_in, lengths unused)
     StreamStep stream;
 };

@@ -107,6 +107,16 @@ __device__ __forceinline__ float raw_or(float a, float b) { return a + b; }     
 __device__ __forceinline__ uint32_t nz_bits(int32_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
+#ifdef SCF_DEBUG_TIMES       // experiment: start / end time of every team (ns, %globaltimer), read back by scf_debug_times
+__device__ unsigned long long g_dbg_times[2 * 2048];
+__device__ __forceinline__ unsigned long long dbg_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int R>
 __device__ __forceinline__ void fft_r(f2 (&x)[R])
 {
@@ -341,6 +351,8 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     // (no zero fill of the exchange area: every float of a valid pair row is rewritten each tile, and whatever an
     //  unused slot holds only reaches that slot's own, discarded, results)
     for (int i = tid; i < n_lq * geo::PPT; i += kThreads) s_logq[i] = pk(0.f, 0.f);
+    if (tid == 0)           // the team's mailbox for drawn tiles (see the tile schedule below): its third tile is fixed
+        *(reinterpret_cast<volatile uint32_t*>(s_bar + 1) + team) = (blockIdx.x * TEAMS + team) + 2 * (gridDim.x * TEAMS);
 
     // pass-2 role of this lane: pair g2 of the warp, column k1
     const int g2 = lane / R;
@@ -374,14 +386,21 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
 
     // ---- where this warp is: its first pair of the current tile as (clip, pair inside the clip), advanced by a fixed
     //      (clips, pairs) step per tile -- one division per kernel instead of three per pair
-    const uint32_t tile_stride = gridDim.x * TEAMS;
+    const uint32_t tile_stride = gridDim.x * TEAMS;          // = number of teams of the grid
     const uint32_t tile_first = blockIdx.x * TEAMS + team;
-    const uint32_t step_pairs = tile_stride * geo::PPT;
-    const uint32_t step_c = fast_div(step_pairs, p.ppc_magic, p.ppc_shift);
-    const uint32_t step_q = step_pairs - step_c * ppc;
-    uint32_t gp0 = tile_first * geo::PPT + warp * geo::G;
-    uint32_t clip0 = fast_div(gp0, p.ppc_magic, p.ppc_shift);
-    uint32_t q0 = gp0 - clip0 * ppc;
+    // Tile schedule.  A team's first three tiles are fixed (tile_first + k * tile_stride); with p.tile_ctr the following
+    // ones come from a global counter, one draw per executed tile and team, three tiles ahead of their use: teams do not
+    // run at the same pace (SMs differ by a few percent), and with a fixed round robin the last team of a 13,229-clip
+    // launch finished 48 us after the first one -- 24 us of idle time per team on average (tools/team_times.py).
+    // Without a counter (streaming steps, generic loader, power output) the round robin continues.
+    uint32_t* const tile_ctr = p.tile_ctr;
+    auto where = [&](uint32_t t, uint32_t& gp, uint32_t& c, uint32_t& q) {      // first pair of this warp in tile t
+        gp = t * geo::PPT + warp * geo::G;
+        c = fast_div(gp, p.ppc_magic, p.ppc_shift);
+        q = gp - c * ppc;
+    };
+    uint32_t gp0, clip0, q0;
+    where(tile_first, gp0, clip0, q0);
     // position of pair g of the warp, given the position of its pair 0
     auto pair_of = [&](uint32_t c_in, uint32_t q_in, int g, uint32_t& c_out, uint32_t& q_out) {
         c_out = c_in;
@@ -557,13 +576,32 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     if (team >= SCF_ABL_TEAMS) return;
 #endif
 
-    for (uint32_t tile = tile_first; tile < n_tiles; tile += tile_stride) {
+#ifdef SCF_DEBUG_TIMES
+    if (tid == 0 && tile_first < 2048) g_dbg_times[tile_first] = dbg_now();
+#endif
+    uint32_t tile = tile_first, tile_n = tile_first + tile_stride, incoming = tile_first + 2 * tile_stride;
+    // s_next: the team's mailbox for drawn tiles.  Thread 0 draws while it has nothing else to do (it holds no DCT
+    // coefficient; log-bank output: behind the log phase) and writes the tile behind the iteration's last barrier but one;
+    // everybody reads the mailbox right behind the NEXT tile's first barrier -- two barriers before the next write.
+    volatile uint32_t* const s_next = reinterpret_cast<volatile uint32_t*>(s_bar + 1) + team;
+    auto draw = [&]() {          // every executed tile draws once: the launch's last number resets the counter
+        const uint32_t v = atomicAdd(tile_ctr, 1u);
+        if (v == n_tiles - 1) *tile_ctr = 0u;
+        *s_next = 3 * tile_stride + v;
+    };
+    auto advance = [&](uint32_t gp_n, uint32_t clip_n, uint32_t q_n) {
+        tile = tile_n;
+        tile_n = incoming;
+        gp0 = gp_n;
+        clip0 = clip_n;
+        q0 = q_n;
+    };
+    while (tile < n_tiles) {
         const uint32_t pair0 = tile * geo::PPT;
         // where this warp will be in its next tile: used for the prefetch now, and as the position then
-        const uint32_t gp_n = gp0 + step_pairs;
-        uint32_t clip_n = clip0 + step_c, q_n = q0 + step_q;
-        if (q_n >= ppc) { q_n -= ppc; ++clip_n; }
-        const bool more = tile + tile_stride < n_tiles;
+        uint32_t gp_n, clip_n, q_n;
+        where(tile_n, gp_n, clip_n, q_n);
+        const bool more = tile_n < n_tiles;
 
         // =========================== FFT stage (per warp) =======================================
         if (gp0 < n_pairs) {
@@ -772,14 +810,13 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             if (lane < geo::G) s_info[warp * geo::G + lane].y = ~0ull;          // no pair, no rows
             if (more) prefetch(gp_n, clip_n, q_n);
         }
-        gp0 = gp_n;
-        clip0 = clip_n;
-        q0 = q_n;
         if (!deps_done) {         // before this grid's first global store
             asm volatile("griddepcontrol.wait;" ::: "memory");
             deps_done = true;
         }
         team_sync();
+        // (through a shuffle: the compiler then knows the value is warp-uniform and keeps the schedule in uniform registers)
+        incoming = tile_ctr != nullptr ? __shfl_sync(0xffffffffu, *s_next, 0) : tile_n + tile_stride;
 
         // =========================== where this thread's pair goes ==============================
         const ulonglong2 info = s_info[slot];                    // (frame energies, row code) from the FFT stage
@@ -802,6 +839,7 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 for (int k = lane; k <= geo::NB; k += 32) dst[k] = silent ? 0.f : src[2 * k] * p.power_scale;
             }
             team_sync();
+            advance(gp_n, clip_n, q_n);
             continue;
         }
 
@@ -938,10 +976,13 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         };
         if (p.out_kind == SCF_OUT_LOG_BANK) {
             if (p.n_peers != 0) push_to_peers();
+            if (tile_ctr != nullptr && tid == 0) draw();
             team_sync();          // the partial-sum rows live in the exchange area: the next tile's pass 1 rewrites them
+            advance(gp_n, clip_n, q_n);
             continue;
         }
         team_sync();
+        if (tile_ctr != nullptr && tid == 0) draw();
 
         // =========================== DCT-II, c0 := log energy ===================================
         // one coefficient of both frames per thread (packed); threads of a quarter warp share the DCT row
@@ -982,7 +1023,11 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         if (p.n_peers != 0) push_to_peers();
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
         // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
+        advance(gp_n, clip_n, q_n);
     }
+#ifdef SCF_DEBUG_TIMES
+    if (tid == 0 && tile_first < 2048) g_dbg_times[2048 + tile_first] = dbg_now();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -991,7 +1036,7 @@ static size_t smem_bytes_rt(const KParams& p)
 {
     using geo = Geo<R>;
     size_t b = (size_t)TEAMS * kWarps * geo::XWARP * 4 + (size_t)((DENSE && TEAMS == 1) ? p.table_small_bytes : p.table_bytes) +
-               (size_t)TEAMS * team_smem_floats<geo::PPT>(p) * 4 + 16;
+               (size_t)TEAMS * team_smem_floats<geo::PPT>(p) * 4 + 32;      // mbarrier (8 bytes) + one next-tile word per team
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1202,6 +1247,13 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+
+#ifdef SCF_DEBUG_TIMES
+extern "C" int scf_debug_times(unsigned long long* out4096)
+{
+    return (int)cudaMemcpyFromSymbol(out4096, g_dbg_times, sizeof(unsigned long long) * 4096);
+}
+#endif
 
 cudaError_t launch_fp32_probe(float* out, int iters, int grid, cudaStream_t st)
 {
