@@ -108,7 +108,7 @@ __device__ __forceinline__ uint32_t nz_bits(int32_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
 #ifdef SCF_DEBUG_TIMES       // experiment: start / end time of every team (ns, %globaltimer), read back by scf_debug_times
-__device__ unsigned long long g_dbg_times[2 * 2048];
+__device__ unsigned long long g_dbg_times[8 * 2048];      // [0] start, [1] end, [2 + i] end of the team's tile i (i < 6)
 __device__ __forceinline__ unsigned long long dbg_now()
 {
     unsigned long long t;
@@ -596,6 +596,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         clip0 = clip_n;
         q0 = q_n;
     };
+#ifdef SCF_DEBUG_TIMES
+    int dbg_i = 0;
+#endif
     while (tile < n_tiles) {
         const uint32_t pair0 = tile * geo::PPT;
         // where this warp will be in its next tile: used for the prefetch now, and as the position then
@@ -1024,6 +1027,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
         // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
         advance(gp_n, clip_n, q_n);
+#ifdef SCF_DEBUG_TIMES
+        if (tid == 0 && tile_first < 2048 && dbg_i < 6) g_dbg_times[(2 + dbg_i++) * 2048 + tile_first] = dbg_now();
+#endif
     }
 #ifdef SCF_DEBUG_TIMES
     if (tid == 0 && tile_first < 2048) g_dbg_times[2048 + tile_first] = dbg_now();
@@ -1249,9 +1255,9 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
 }
 
 #ifdef SCF_DEBUG_TIMES
-extern "C" int scf_debug_times(unsigned long long* out4096)
+extern "C" int scf_debug_times(unsigned long long* out4096)      // 8 x 2048 values
 {
-    return (int)cudaMemcpyFromSymbol(out4096, g_dbg_times, sizeof(unsigned long long) * 4096);
+    return (int)cudaMemcpyFromSymbol(out4096, g_dbg_times, sizeof(unsigned long long) * 8 * 2048);
 }
 #endif
 

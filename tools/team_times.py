@@ -20,7 +20,7 @@ pcm = torch.randint(-32768, 32768, (n, 16000), dtype=torch.int16, device='cuda',
 out = torch.empty((n, 30, 20), dtype=torch.float32, device='cuda')
 st = torch.cuda.current_stream()
 L = ctypes.CDLL(_lib.LIB_PATH)
-buf = (ctypes.c_ulonglong * 4096)()
+buf = (ctypes.c_ulonglong * (8 * 2048))()
 for rep in range(4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -36,3 +36,14 @@ for rep in range(4):
           '(spread %.1f us, mean idle %.1f us per team)' % (rep, e0.elapsed_time(e1) * 1e3, (s.max() - t0) / 1e3, (e.min() - t0) / 1e3,
                                                              float(np.median(e) - t0) / 1e3, (e.max() - t0) / 1e3, (e.max() - e.min()) / 1e3,
                                                              float((e.max() - e).mean()) / 1e3))
+    tiles = t[2 * 2048:].reshape(6, 2048)[:, :n_teams]
+    prev = s
+    row = []
+    for i in range(6):
+        ok = tiles[i] > 0
+        if not ok.any():
+            break
+        d = (tiles[i] - prev)[ok] / 1e3
+        row.append('tile %d: %.1f us (min %.1f max %.1f)' % (i, float(np.median(d)), d.min(), d.max()))
+        prev = tiles[i]
+    print('      per-team tile durations, median: ' + '; '.join(row))
