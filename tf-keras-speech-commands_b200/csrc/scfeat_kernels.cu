@@ -1046,7 +1046,7 @@ static size_t smem_bytes_rt(const KParams& p)
     return (b + 15) & ~(size_t)15;
 }
 
-constexpr int64_t kTeamsMinPairs = 23040;      // measured crossover vs the 3-CTA variant: ~1500 one-second clips (tools/sweep.py)
+constexpr int64_t kTeamsMinPairs = 30720;      // measured crossover vs the 3-CTA variant: ~2000 one-second clips (tools/sweep.py)
 constexpr size_t kSmemPerSm = 233472, kSmemReserve = 1024, kSmemMaxBlock = 232448;
 
 // Kernel variant for a launch (see the template's comment): 0 = classic, 1 = dense with 3 CTAs per SM (n_fft = 1024

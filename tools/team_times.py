@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Start / end times of every team of one large launch (variant built with -DSCF_DEBUG_TIMES): how far apart the teams
-finish under the static round-robin tile assignment.  Usage: SCFEAT_LIB=.../libscfeat_dbgtimes.so python tools/team_times.py [clips]"""
+finish under the static round-robin tile assignment.  Usage: SCFEAT_LIB=.../libscfeat_dbgtimes.so python tools/team_times.py [clips [launches back to back]]"""
 import ctypes
 import os
 import sys
@@ -13,6 +13,7 @@ import scfeat
 from scfeat import _lib
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 13229
+chain = int(sys.argv[2]) if len(sys.argv) > 2 else 1          # launches issued back to back; the last one is reported
 plan = scfeat.get_plan()
 g = torch.Generator(device='cuda')
 g.manual_seed(0)
@@ -24,7 +25,8 @@ buf = (ctypes.c_ulonglong * (8 * 2048))()
 for rep in range(4):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    plan.extract_device(pcm.data_ptr(), n, 16000, out.data_ptr(), stream=st.cuda_stream)
+    for _ in range(chain):
+        plan.extract_device(pcm.data_ptr(), n, 16000, out.data_ptr(), stream=st.cuda_stream)
     e1.record()
     torch.cuda.synchronize()
     assert L.scf_debug_times(buf) == 0
