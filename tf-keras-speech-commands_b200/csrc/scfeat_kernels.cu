@@ -109,6 +109,7 @@ __device__ __forceinline__ uint32_t nz_bits(float v) { return __float_as_uint(v)
 
 #ifdef SCF_DEBUG_TIMES       // experiment: start / end time of every team (ns, %globaltimer), read back by scf_debug_times
 __device__ unsigned long long g_dbg_times[8 * 2048];      // [0] start, [1] end, [2 + i] end of the team's tile i (i < 6)
+__device__ unsigned long long g_dbg_phase[2 * 8 * 2048];  // [thread 0 | thread 224][phase][team]: SM cycles summed over tiles
 __device__ __forceinline__ unsigned long long dbg_now()
 {
     unsigned long long t;
@@ -598,6 +599,16 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
     };
 #ifdef SCF_DEBUG_TIMES
     int dbg_i = 0;
+    auto dbg_clock = []() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; };
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = dbg_clock();
+    // phases: 0 FFT stage, 1 wait at the first barrier, 2 bank, 3 wait at the second barrier, 4 log, 5 wait at the third, 6 DCT + stores
+#define DBG_MARK(ph) do { const long long now_ = dbg_clock(); dbg_acc[ph] += now_ - dbg_t; dbg_t = now_; } while (0)
+    // behind a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on until its next memory access, so read something first
+#define DBG_MARK_SYNCED(ph) do { int probe_; asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(probe_) : "r"(smem_u32(s_bar)) : "memory"); \
+        asm volatile("" :: "r"(probe_) : "memory"); DBG_MARK(ph); } while (0)
+#else
+#define DBG_MARK_SYNCED(ph) do { } while (0)
+#define DBG_MARK(ph) do { } while (0)
 #endif
     while (tile < n_tiles) {
         const uint32_t pair0 = tile * geo::PPT;
@@ -817,7 +828,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             asm volatile("griddepcontrol.wait;" ::: "memory");
             deps_done = true;
         }
+        DBG_MARK(0);
         team_sync();
+        DBG_MARK_SYNCED(1);
         // (through a shuffle: the compiler then knows the value is warp-uniform and keeps the schedule in uniform registers)
         incoming = tile_ctr != nullptr ? __shfl_sync(0xffffffffu, *s_next, 0) : tile_n + tile_stride;
 
@@ -896,7 +909,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 run_task(tk.x, x, wx);
             }
         }
+        DBG_MARK(2);
         team_sync();
+        DBG_MARK_SYNCED(3);
 
         // =========================== log ========================================================
         const f2 frame_energy = info.x;
@@ -984,7 +999,9 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
             advance(gp_n, clip_n, q_n);
             continue;
         }
+        DBG_MARK(4);
         team_sync();
+        DBG_MARK_SYNCED(5);
         if (tile_ctr != nullptr && tid == 0) draw();
 
         // =========================== DCT-II, c0 := log energy ===================================
@@ -1027,10 +1044,15 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
         // no barrier needed here: the next tile's FFT stage touches only the exchange area, which no thread reads
         // after the log phase; s_logq / s_info / s_stage are rewritten only behind later barriers.
         advance(gp_n, clip_n, q_n);
+        DBG_MARK(6);
 #ifdef SCF_DEBUG_TIMES
         if (tid == 0 && tile_first < 2048 && dbg_i < 6) g_dbg_times[(2 + dbg_i++) * 2048 + tile_first] = dbg_now();
 #endif
     }
+#ifdef SCF_DEBUG_TIMES
+    if ((tid == 0 || tid == 224) && tile_first < 2048)
+        for (int ph = 0; ph < 8; ++ph) g_dbg_phase[((tid ? 1 : 0) * 8 + ph) * 2048 + tile_first] = (unsigned long long)dbg_acc[ph];
+#endif
 #ifdef SCF_DEBUG_TIMES
     if (tid == 0 && tile_first < 2048) g_dbg_times[2048 + tile_first] = dbg_now();
 #endif
@@ -1255,6 +1277,10 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
 }
 
 #ifdef SCF_DEBUG_TIMES
+extern "C" int scf_debug_phases(unsigned long long* out)         // 2 x 8 x 2048 values
+{
+    return (int)cudaMemcpyFromSymbol(out, g_dbg_phase, sizeof(unsigned long long) * 2 * 8 * 2048);
+}
 extern "C" int scf_debug_times(unsigned long long* out4096)      // 8 x 2048 values
 {
     return (int)cudaMemcpyFromSymbol(out4096, g_dbg_times, sizeof(unsigned long long) * 8 * 2048);

@@ -49,3 +49,12 @@ for rep in range(4):
         row.append('tile %d: %.1f us (min %.1f max %.1f)' % (i, float(np.median(d)), d.min(), d.max()))
         prev = tiles[i]
     print('      per-team tile durations, median: ' + '; '.join(row))
+    pbuf = (ctypes.c_ulonglong * (2 * 8 * 2048))()
+    if hasattr(L, 'scf_debug_phases') and L.scf_debug_phases(pbuf) == 0 and rep == 3:
+        ph = np.frombuffer(pbuf, dtype=np.uint64).astype(np.float64).reshape(2, 8, 2048)[:, :7, :n_teams]
+        names = ['FFT stage', 'wait 1st barrier', 'bank', 'wait 2nd barrier', 'log', 'wait 3rd barrier', 'DCT + stores + bookkeeping']
+        for w, who in enumerate(('thread 0 (warp 0: no DCT coefficient)', 'thread 224 (warp 7: no log band)')):
+            tot = ph[w].sum(axis=0)
+            share = ph[w].sum(axis=1) / tot.sum()
+            print('      %s: ' % who + ', '.join('%s %.1f %%' % (nm, 100 * x) for nm, x in zip(names, share)) +
+                  ' | %.0f cycles per tile' % (tot.mean() / max(1.0, (n * 15 / 8) / n_teams)))
