@@ -10,9 +10,12 @@
 //
 // Resampling is out of scope (the reference leaves it to librosa): a file whose rate differs from the plan's is an error.
 #include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -76,8 +79,79 @@ static bool parse_wav(FILE* f, WavInfo& w, std::string& why)
     }
 }
 
+// The same chunk walk over the first bytes of a file already in memory; false when the data chunk does not start inside
+// them (the caller then takes the stdio path).
+static bool parse_wav_mem(const unsigned char* b, size_t n, WavInfo& w, std::string& why, bool& fatal)
+{
+    fatal = true;
+    if (n < 12 || memcmp(b, "RIFF", 4) != 0 || memcmp(b + 8, "WAVE", 4) != 0) { why = "not a RIFF/WAVE file"; return false; }
+    bool have_fmt = false;
+    size_t o = 12;
+    for (;;) {
+        if (o + 8 > n) { fatal = false; return false; }           // header longer than what was read: not an error yet
+        const uint32_t size = le32(b + o + 4);
+        if (memcmp(b + o, "fmt ", 4) == 0) {
+            if (size < 16) { why = "short fmt chunk"; return false; }
+            if (o + 8 + std::min<size_t>(size, 40) > n) { fatal = false; return false; }
+            const unsigned char* c = b + o + 8;
+            w.format = (int)le16(c);
+            w.channels = (int)le16(c + 2);
+            w.rate = (int)le32(c + 4);
+            w.bits = (int)le16(c + 14);
+            if (w.format == 0xFFFE && size >= 26) w.format = (int)le16(c + 24);    // WAVE_FORMAT_EXTENSIBLE: sub-format
+            have_fmt = true;
+        } else if (memcmp(b + o, "data", 4) == 0) {
+            if (!have_fmt) { why = "data chunk before fmt chunk"; return false; }
+            w.data_off = (long)(o + 8);
+            w.data_bytes = size;
+            fatal = false;
+            return true;
+        }
+        o += 8 + (size_t)size + (size & 1);
+    }
+}
+
+static int read_one_stdio(const char* path, int sample_rate, int clip_len, int16_t* dst, std::vector<int16_t>& scratch, std::string& why);
+
 // One file -> row `dst` (clip_len samples, zero filled behind the data); returns the number of valid samples or -1.
+// Fast path: open + ONE read of header and samples into a per-thread buffer + close (three system calls instead of the
+// five of the stdio path: fopen's fstat, a 4 KB header read and the data read), header parsed in memory.
 static int read_one(const char* path, int sample_rate, int clip_len, int16_t* dst, std::vector<int16_t>& scratch, std::string& why)
+{
+    constexpr size_t kHead = 4096;                                  // room for the chunks in front of the samples
+    const size_t cap = kHead + (size_t)clip_len * 2;
+    if (scratch.size() * 2 < cap) scratch.resize((cap + 1) / 2);
+    unsigned char* buf = reinterpret_cast<unsigned char*>(scratch.data());
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) { why = "cannot open"; return -1; }
+    size_t n = 0;
+    for (;;) {                                                      // (a regular file hands everything over in one call)
+        const ssize_t r = read(fd, buf + n, cap - n);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) break;
+        n += (size_t)r;
+        if (n == cap) break;
+    }
+    close(fd);
+    WavInfo w;
+    bool fatal = false;
+    if (!parse_wav_mem(buf, n, w, why, fatal)) {
+        if (fatal) return -1;
+        return read_one_stdio(path, sample_rate, clip_len, dst, scratch, why);      // long header: the general path
+    }
+    if (w.channels != 1 || w.format != 1 || w.bits != 16 || w.rate != sample_rate)
+        return read_one_stdio(path, sample_rate, clip_len, dst, scratch, why);      // mix-down and the error texts live there
+    const long long frames_in_file = w.data_bytes / 2;
+    const int want = (int)std::min<long long>(frames_in_file, clip_len);
+    const size_t have = n > (size_t)w.data_off ? (n - (size_t)w.data_off) / 2 : 0;
+    if ((size_t)want > have && n == cap) return read_one_stdio(path, sample_rate, clip_len, dst, scratch, why);
+    const int got = (int)std::min<size_t>((size_t)want, have);      // a truncated file gives what it has, like fread
+    memcpy(dst, buf + w.data_off, (size_t)got * 2);
+    if (got < clip_len) memset(dst + got, 0, (size_t)(clip_len - got) * 2);
+    return got;
+}
+
+static int read_one_stdio(const char* path, int sample_rate, int clip_len, int16_t* dst, std::vector<int16_t>& scratch, std::string& why)
 {
     FILE* f = fopen(path, "rb");
     if (!f) { why = "cannot open"; return -1; }
