@@ -287,3 +287,24 @@ def test_parallel_memcpy_sizes_and_concurrent_callers():
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs
+
+
+def test_parallel_memcpy_in_a_forked_child():
+    """A forked child inherits the copy pool's bookkeeping but not its threads: it must copy on its own and exit cleanly."""
+    import multiprocessing as mp
+    L = _lib.lib()
+    src = np.arange(2_000_000, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    _lib.check(L.scf_parallel_memcpy(dst.ctypes.data, src.ctypes.data, src.size))      # the pool exists in the parent
+
+    def child(q):
+        d = np.zeros_like(src)
+        rc = L.scf_parallel_memcpy(d.ctypes.data, src.ctypes.data, src.size)
+        q.put((rc, bool(np.array_equal(d, src))))
+    ctx = mp.get_context('fork')
+    q = ctx.Queue()
+    p = ctx.Process(target=child, args=(q,))
+    p.start()
+    rc, same = q.get(timeout=60)
+    p.join(timeout=60)
+    assert rc == 0 and same and p.exitcode == 0

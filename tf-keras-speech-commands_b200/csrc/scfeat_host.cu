@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -209,7 +210,8 @@ public:
     void copy(void* dst, const void* src, size_t bytes)
     {
         constexpr size_t kMinPart = 256 * 1024;
-        const size_t parts = std::max<size_t>(1, std::min<size_t>(workers_.size() + 1, bytes / kMinPart));
+        const size_t helpers = getpid() == owner_ ? workers_.size() : 0;      // (a forked child has no worker threads)
+        const size_t parts = std::max<size_t>(1, std::min<size_t>(helpers + 1, bytes / kMinPart));
         if (parts == 1) {
             memcpy(dst, src, bytes);
             return;
@@ -243,10 +245,15 @@ private:
             int cores = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
             n = std::max(1, std::min(8, cores / 2));
         }
+        owner_ = getpid();
         for (int i = 1; i < n; ++i) workers_.emplace_back([this] { run(); });
     }
     ~CopyPool()
     {
+        if (getpid() != owner_) {               // a forked child inherits the objects but not the threads
+            for (auto& t : workers_) t.detach();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(mu_);
             stop_ = true;
@@ -272,6 +279,7 @@ private:
     std::condition_variable cv_, done_;
     std::deque<Job> q_;
     std::vector<std::thread> workers_;
+    pid_t owner_ = 0;
     bool stop_ = false;
 };
 
