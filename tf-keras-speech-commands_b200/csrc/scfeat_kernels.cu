@@ -118,6 +118,14 @@ __device__ __forceinline__ unsigned long long dbg_now()
 }
 #endif
 
+// natural logarithm of a normal, positive float
+__device__ __forceinline__ float log_ge_eps(float x)
+{
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    return l * 0.6931471805599453f;
+}
+
 template <int R>
 __device__ __forceinline__ void fft_r(f2 (&x)[R])
 {
@@ -928,9 +936,10 @@ __global__ void __launch_bounds__(kThreads* TEAMS, TEAMS == 3 ? 1 : (DENSE ? 3 :
                 const f2* pr = part(qs.x);
                 for (int j = 0; j < qs.y; ++j) v = add2(v, pr[j * (geo::PPT)]);
             }
-            // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3
-            const float la = __logf(fmaxf(silent_a ? 0.f : lo(v), SCF_EPS));
-            const float lb = __logf(fmaxf(silent_b ? 0.f : hi(v), SCF_EPS));
+            // lg2.approx * ln2: |err| ~ 1e-6, budget 1e-3 (.ftz: the argument is >= eps, so the denormal range check and
+            // rescaling that __logf wraps around the MUFU are dead weight -- 8 instructions per thread on this phase's path)
+            const float la = log_ge_eps(fmaxf(silent_a ? 0.f : lo(v), SCF_EPS));
+            const float lb = log_ge_eps(fmaxf(silent_b ? 0.f : hi(v), SCF_EPS));
             if (p.out_kind == SCF_OUT_LOG_BANK) {
                 if (p.n_peers != 0) {                          // staged for the coalesced peer stores below
                     s_stage[(2 * slot) * p.out_cols + q] = la;
