@@ -357,6 +357,8 @@ struct scf_stream {
     int max_chunk = 0;
     int16_t* d_chunk_stage = nullptr;     // for the host-buffer push
     scf::MappedStage small;               // ... of few streams (chunk in, ring + counters out through mapped memory)
+    unsigned char* pin = nullptr;         // ... of many streams: pinned chunk / ring / counter staging
+    size_t pin_bytes = 0;
 };
 
 namespace scf {
@@ -1542,6 +1544,7 @@ void scf_stream_destroy(scf_stream* s)
     cudaFree(s->n_new);
     cudaFree(s->d_chunk_stage);
     s->small.release();
+    if (s->pin) cudaFreeHost(s->pin);
     delete s;
 }
 
@@ -1612,19 +1615,36 @@ int scf_stream_push_host_i16(scf_stream* s, const int16_t* h_chunks, int32_t chu
             return SCF_OK;
         }
     }
-    SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, h_chunks, (size_t)s->n_streams * chunk_len * 2, cudaMemcpyHostToDevice, nullptr));
+    // Many streams: the caller's (pageable) chunk and ring arrays go through the stream object's own pinned buffers, moved
+    // by the copy threads -- copies from / to pageable memory are bounce copies inside the driver and made this call
+    // 237 us for 256 streams, of which the step itself is 20.
+    const size_t cbytes = (size_t)s->n_streams * chunk_len * 2;
+    const size_t rbytes = (size_t)s->n_streams * s->ring_rows * s->plan->out_cols * 4;
+    const size_t nbytes = (size_t)s->n_streams * 4;
+    const size_t c_al = (cbytes + 255) & ~(size_t)255, r_al = (rbytes + 255) & ~(size_t)255;
+    if (!s->pin || s->pin_bytes < c_al + r_al + nbytes) {
+        if (s->pin) cudaFreeHost(s->pin);
+        s->pin = nullptr;
+        s->pin_bytes = 0;
+        const size_t want = (((size_t)s->n_streams * s->max_chunk * 2 + 255) & ~(size_t)255) + r_al + nbytes;
+        SCF_CUDA(cudaHostAlloc((void**)&s->pin, want, cudaHostAllocDefault));
+        s->pin_bytes = want;
+    }
+    CopyPool& pool = CopyPool::get();
+    pool.copy(s->pin, h_chunks, cbytes);
+    SCF_CUDA(cudaMemcpyAsync(s->d_chunk_stage, s->pin, cbytes, cudaMemcpyHostToDevice, nullptr));
     // delta plans hand out wide rows: the step writes them (and their delta columns) into the stream's wide copy
     float* wide = (h_ring_out && s->ring_wide) ? s->ring_wide : nullptr;
     int rc = scf_stream_push_i16(s, s->d_chunk_stage, chunk_len, wide, nullptr, nullptr);
     if (rc) return rc;
     if (h_ring_out) {       // the new ring is the state buffer the push just wrote (or its wide copy)
         const float* src = wide ? wide : s->ring[s->cur];
-        SCF_CUDA(cudaMemcpyAsync(h_ring_out, src, (size_t)s->n_streams * s->ring_rows * s->plan->out_cols * 4,
-                                 cudaMemcpyDeviceToHost, nullptr));
+        SCF_CUDA(cudaMemcpyAsync(s->pin + c_al, src, rbytes, cudaMemcpyDeviceToHost, nullptr));
     }
-    if (h_new_rows)
-        SCF_CUDA(cudaMemcpyAsync(h_new_rows, s->n_new, (size_t)s->n_streams * 4, cudaMemcpyDeviceToHost, nullptr));
+    if (h_new_rows) SCF_CUDA(cudaMemcpyAsync(s->pin + c_al + r_al, s->n_new, nbytes, cudaMemcpyDeviceToHost, nullptr));
     SCF_CUDA(cudaStreamSynchronize(nullptr));
+    if (h_ring_out) pool.copy(h_ring_out, s->pin + c_al, rbytes);
+    if (h_new_rows) memcpy(h_new_rows, s->pin + c_al + r_al, nbytes);
     return SCF_OK;
 }
 
