@@ -322,7 +322,7 @@ struct IngestStage {
     }
 };
 
-IngestStage g_stage;
+IngestStage g_stage;      // lives as long as the process (no CUDA calls from a static destructor); 3 x (batch x 32 KB) pinned
 
 int ingest_core(const scf_plan* plan, const char* const* paths, int64_t n_files, int32_t clip_len, int32_t batch,
                 int32_t n_threads, float* h_out, float* d_out, int32_t* h_lengths_out)
