@@ -693,6 +693,19 @@ def test_dynamic_tile_schedule_equals_round_robin(example_pcm):
     assert_cepstrum_close(scfeat.get_plan().extract_host(clips)[::997], want)
 
 
+def test_randomised_self_consistency_stress():
+    """tools/stress_schedule.py: random plans (FFT size, bank, filters, coefficients, output kind, front end) and job
+    shapes; one big launch (dynamic tile schedule) equals small launches (round robin) bit for bit, streams match the
+    batch features of their concatenated audio."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'stress_schedule.py'), '12', '7'], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and 'STRESS_OK' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_one_plan_shared_by_threads_and_streams(example_pcm):
     """include/scfeat.h: plans are immutable and may be shared between threads.  Four threads drive the same plan on
     their own CUDA streams (device API) and through the host-buffer API at once; every result must equal the
